@@ -1,0 +1,268 @@
+/*
+ * ogpu.h — C ABI of libogpu.so: the B200-native scan/aggregate path behind openGemini's
+ * cursor seam.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (paths relative to the openGemini tree):
+ *
+ *   og_shard_open            engine/immutable/tssp_reader.go:118,586 (TSSPFile.ReadAt: locate pages through
+ *                            ChunkMeta.colMeta[i].entries[seg]{offset,size}, tssp_file_meta.go:60-63,377-385)
+ *                            + lib/fileops/readcache page access.  Here: one upload of the data region + the
+ *                            flattened ChunkMeta ("segment directory") into HBM.
+ *   og_query_create/run      engine/iterators.go:130 shard.CreateCursor -> createGroupCursors :551 ->
+ *                            NewAggregateCursor aggregate_cursor.go:65 + NewAggTagSetCursor agg_tagset_cursor.go:583;
+ *                            SinkPlan (aggregate_cursor.go:208) builds what og_query_desc carries.
+ *   og_query_next            comm.KeyCursor.Next / NextAggData (engine/comm/cursor.go:46-56) as drained by
+ *                            ChunkReader.nextRecord (engine/iterator_plan.go:707-717): returns ColVal-shaped
+ *                            views (lib/record/column.go:30-37) valid until the next call, like
+ *                            record.CircularRecordPool (lib/record/record_pool.go:208-268).
+ *   og_query_dense           the dense interval record AggTagSetCursor builds (agg_tagset_cursor.go:1012-1027,
+ *                            lib/record/record.go:1327 BuildEmptyIntervalRec) — exposed as device arrays so the
+ *                            cross-shard merge (engine/executor/rpc_transform.go:40-282 + agg_transform.go:248-304
+ *                            in the reference) can be an NCCL all-reduce.
+ *   og_decode_segment        engine/immutable/reader.go:674 decodeColumnData + append{Integer,Float,Boolean}Column
+ *                            :504-579 + appendTimeColumnData :638 (Record materialisation for
+ *                            HybridStoreReader-style callers, engine/hybrid_store_reader.go:444).
+ *   og_encode_pages          engine/immutable/column_builder.go:151-349 enc*Column + EncodeColumnHeader :428,
+ *                            chunkdata_builder.go:65 EncodeTime (downsample / compaction re-encode).
+ *   og_shard_synth           test/bench tooling: builds a synthetic shard directly in HBM with the encode kernels
+ *                            (same bytes the oracle's restated encoders produce; see tests/test_synth_parity.py).
+ *
+ * Conventions (modelled on the in-tree cgo precedents engine/index/textindex/textbuilder_c.h:20-28 and
+ * lib/util/lifted/encoding/lz4/lz4_linux_amd64.go:18-30): opaque handles, caller-owned inputs, library-owned
+ * outputs, int status returns, no callbacks, no retained caller pointers after a call returns (og_shard_open
+ * copies what it needs).  A handle is confined to one thread at a time; distinct queries may run concurrently.
+ * There is NO CPU fallback: every compute entry point returns OG_E_CUDA when no device is bound.
+ */
+#ifndef OGPU_H
+#define OGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OG_API __attribute__((visibility("default")))
+
+/* ---- status codes (errors are codes, never panics across cgo) ---- */
+enum {
+    OG_OK = 0,
+    OG_EOF = 1,            /* og_query_next: end of stream, the (nil,nil,nil) of KeyCursor.Next */
+    OG_E_INVAL = -1,       /* bad argument / descriptor */
+    OG_E_CUDA = -2,        /* CUDA runtime failure or no device bound */
+    OG_E_NOMEM = -3,
+    OG_E_UNSUPPORTED = -4, /* codec tag / option recognised but not implemented on the GPU path (zstd, mlf, lz4, descending, DST location) */
+    OG_E_CORRUPT = -5,     /* page failed validation (lib/errno InvalidFloatBuffer etc.) */
+    OG_E_ABORTED = -6,     /* og_query_abort was called (closedSignal, engine/immutable/read_context.go:68-70) */
+    OG_E_TYPE = -7,        /* "type(%v) in table not eq select type(%v)" column_builder.go:466 */
+    OG_E_STATE = -8        /* call sequence error (next before run, ...) */
+};
+
+/* ---- column types: influx.Field_Type_* (lib/util/lifted/vm/protoparser/influx/parser.go:1363-1370) ---- */
+enum { OG_TYPE_INT = 1, OG_TYPE_FLOAT = 3, OG_TYPE_STRING = 4, OG_TYPE_BOOL = 5 };
+
+/* ---- aggregate calls pushed down to the store (engine/series_call_processor.go:56-80).
+ *      mean() never arrives: the planner rewrites it to sum/count (engine/executor/schema.go:376-418). ---- */
+enum { OG_AGG_COUNT = 1, OG_AGG_SUM = 2, OG_AGG_MIN = 3, OG_AGG_MAX = 4, OG_AGG_FIRST = 5, OG_AGG_LAST = 6 };
+
+/* ---- WHERE filter: RPN over per-column compare terms (lib/binaryfilterfunc/functions.go:632, lib/rpn) ---- */
+enum { OG_F_TERM = 0, OG_F_AND = 1, OG_F_OR = 2 };
+enum { OG_OP_LT = 0, OG_OP_LTE = 1, OG_OP_GT = 2, OG_OP_GTE = 3, OG_OP_EQ = 4, OG_OP_NEQ = 5 };
+
+typedef struct og_filter_item {
+    int32_t kind;           /* OG_F_TERM / OG_F_AND / OG_F_OR */
+    int32_t column;         /* field column index (TERM only) */
+    int32_t op;             /* OG_OP_* (TERM only) */
+    int32_t const_is_float; /* 1: compare against fval (int columns are converted with Int64ToFloat64Slice, functions.go:439); 0: ival */
+    double fval;
+    int64_t ival;           /* int constant, or 0/1 for bool columns */
+} og_filter_item;
+
+typedef struct og_call {
+    int32_t func;   /* OG_AGG_* */
+    int32_t column; /* field column index in the shard */
+} og_call;
+
+enum { OG_GROUP_ALL = 0, OG_GROUP_PER_SERIES = 1, OG_GROUP_MAP = 2 };
+enum {
+    OG_Q_STRICT_ORDER = 1u << 0 /* cross-series float sums in strict series order (bit-exact with the reference's
+                                   sequential merge, lib/record/reccord_functions.go:730-733) instead of chunked order */
+};
+
+typedef struct og_query_desc {
+    int64_t interval;  /* GROUP BY time() duration in ns; 0 = no interval (one window = [tmin, tmax]) */
+    int64_t offset;    /* hybridqp.Interval.Offset */
+    int64_t tmin, tmax;/* inclusive query time range (util.TimeRange) */
+    int32_t ascending; /* must be 1; descending scans return OG_E_UNSUPPORTED (SURVEY App.B.14) */
+    uint32_t n_calls;
+    const og_call *calls;
+    uint32_t n_filter; /* 0 = no WHERE on fields */
+    const og_filter_item *filter;
+    int32_t group_mode; /* OG_GROUP_* : how series map to tagsets */
+    uint32_t n_groups;  /* OG_GROUP_MAP only */
+    const uint32_t *series_group; /* OG_GROUP_MAP: [n_series] group id per series (series order inside a group = shard order) */
+    int32_t chunk_size; /* ChunkSizeNum: max rows per record returned by og_query_next (<=0: 1024) */
+    uint32_t flags;     /* OG_Q_* */
+} og_query_desc;
+
+/* ---- shard description = TSSP data region + flattened ChunkMeta ---- */
+typedef struct og_column_desc {
+    const char *name;         /* column name (schema order = sorted by name, time last: lib/record/record.go:115-123) */
+    int32_t type;             /* OG_TYPE_* */
+    const uint64_t *page_off; /* [n_segments] byte offset of this column's page (segment) inside data; Segment.offset */
+    const uint32_t *page_len; /* [n_segments] Segment.size; 0 = column absent in that chunk (all rows null) */
+} og_column_desc;
+
+enum {
+    OG_SHARD_DEVICE_DATA = 1u << 0 /* `data` is a device pointer owned by the caller for the shard's lifetime (zero-copy) */
+};
+
+typedef struct og_shard_desc {
+    const uint8_t *data; /* file bytes that the page offsets index (whole file or data region) */
+    uint64_t data_len;
+    uint32_t n_series;   /* chunks; one series id each (ChunkMeta.sid) */
+    const uint64_t *sids;              /* [n_series] */
+    const uint32_t *series_seg_begin;  /* [n_series+1] first segment index of each series; segments of a series are
+                                          consecutive and time-ordered (chunkdata_builder_ts.go:36-82) */
+    uint32_t n_segments;
+    const int64_t *seg_tmin;           /* [n_segments] ChunkMeta.timeRange[seg] */
+    const int64_t *seg_tmax;
+    uint32_t n_columns;                /* field columns (time excluded) */
+    const og_column_desc *columns;
+    const uint64_t *time_page_off;     /* [n_segments] time column pages */
+    const uint32_t *time_page_len;
+    uint32_t flags;                    /* OG_SHARD_* */
+} og_shard_desc;
+
+/* ---- ColVal / Record views (lib/record/column.go:30-37, record.go:57-61) ---- */
+typedef struct og_colval_view {
+    const uint8_t *val;     /* dense interval records: one slot per row (AppendXxxNullReserve layout, record.go:1298-1338);
+                               decoded segments: non-null values only, densely packed LE (reader.go:504-579) */
+    uint64_t val_bytes;
+    const uint8_t *bitmap;  /* LSB-first, 1 = present, bit index = bitmap_offset + row (column.go:26-28,489-498) */
+    const int64_t *times;   /* RecMeta.Times[col] for first/last in multi-call queries, else NULL */
+    int32_t type;           /* OG_TYPE_* of the output column (count -> INT) */
+    int32_t len;
+    int32_t nil_count;
+    int32_t bitmap_offset;
+} og_colval_view;
+
+typedef struct og_record_view {
+    uint32_t n_cols;
+    const og_colval_view *cols; /* field columns in call order */
+    const int64_t *times;       /* time column (always full) */
+    int32_t rows;
+    uint32_t group;             /* tagset / group id this record belongs to */
+    uint64_t sid;               /* OG_GROUP_PER_SERIES: series id */
+} og_record_view;
+
+/* dense interval record on the device: what leaves AggTagSetCursor before TransIntervalRec2Rec */
+typedef struct og_dense_col {
+    void *values;    /* device, [n_groups * n_buckets] 8-byte cells (bool min/max/first/last stored as int64 0/1) */
+    uint8_t *valid;  /* device, [n_groups * n_buckets] 1 = non-null */
+    int64_t *times;  /* device, [n_groups * n_buckets] row time carried by selectors (min/max/first/last); NULL for sum/count */
+    int32_t type;    /* OG_TYPE_* of the value cells */
+    int32_t func;
+} og_dense_col;
+
+typedef struct og_dense_view {
+    uint32_t n_groups;
+    uint32_t n_buckets;
+    int64_t start;     /* window start of bucket 0 (TimeWindowsInit, agg_tagset_cursor.go:1012) */
+    int64_t interval;
+    uint32_t n_cols;
+    const og_dense_col *cols; /* host array of device pointers */
+    void *stream;      /* cudaStream_t the arrays were produced on (already synchronised when run returns) */
+} og_dense_view;
+
+typedef struct og_stats {
+    uint64_t rows_decoded;     /* rows in every decoded segment (SURVEY §8d row definition) */
+    uint64_t segments_scanned; /* after time-range pruning (location.go:276-280) */
+    uint64_t page_bytes;       /* algorithmic input bytes: value + time pages of scanned segments */
+    uint64_t dir_bytes;        /* directory bytes read */
+    uint64_t out_bytes;        /* dense output bytes */
+    double kernel_ms;          /* device time of the last og_query_run (CUDA events on the query stream) */
+    double h2d_ms;
+    uint32_t kernel_launches;  /* kernels launched by the last og_query_run */
+} og_stats;
+
+typedef struct og_shard og_shard;
+typedef struct og_query og_query;
+
+/* ---- lifecycle ---- */
+OG_API int og_init(int device_ordinal);            /* bind the calling process to a device; idempotent */
+OG_API int og_device_count(void);
+OG_API const char *og_strerror(int status);
+OG_API const char *og_last_error(void);            /* thread-local detail message of the last failing call */
+OG_API const char *og_version(void);
+
+/* ---- shard ---- */
+OG_API int og_shard_open(const og_shard_desc *desc, og_shard **out);
+OG_API void og_shard_close(og_shard *s);
+OG_API int og_shard_info(const og_shard *s, uint64_t *n_series, uint64_t *n_segments, uint64_t *n_rows,
+                         uint64_t *page_bytes, int64_t *tmin, int64_t *tmax);
+
+/* ---- query (aggregate cursor tree) ---- */
+OG_API int og_query_create(og_shard *s, const og_query_desc *desc, og_query **out);
+OG_API int og_query_run(og_query *q);              /* launches the decode+aggregate kernels and waits for them */
+OG_API int og_query_next(og_query *q, og_record_view *out); /* OG_OK + record, or OG_EOF */
+OG_API int og_query_dense(og_query *q, og_dense_view *out);
+OG_API int og_query_stats(const og_query *q, og_stats *out);
+OG_API void og_query_abort(og_query *q);
+OG_API void og_query_destroy(og_query *q);
+
+/* merge another shard's dense partial (same query shape) into q's dense result on the device:
+ * used after an all-gather for selector aggregates whose (value,time) tie-breaks are not a plain NCCL op
+ * (lib/record/reccord_functions.go:482-494).  `other` holds device pointers laid out like og_query_dense's. */
+OG_API int og_query_merge_dense(og_query *q, const og_dense_view *other);
+
+/* ---- materialise path (KeyCursor.Next for non-aggregating callers) ---- */
+OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out);
+/* decode a range of segments of one column into caller-provided DEVICE buffers (dense values, 8 B or 1 B each);
+ * rows_out[i] receives the non-null value count of segment seg_begin+i. column == n_columns selects time. */
+OG_API int og_decode_column_device(og_shard *s, uint32_t column, uint32_t seg_begin, uint32_t seg_end,
+                                   void *d_values, uint64_t value_stride_bytes, uint32_t *d_rows_out);
+
+/* ---- synthetic shard built on the device (bench/test tooling; uses the encode kernels) ---- */
+enum { OG_SYNTH_F_HI = 0, OG_SYNTH_F_LO = 1, OG_SYNTH_INT_WALK = 2, OG_SYNTH_BOOL = 3 };
+typedef struct og_synth_column {
+    int32_t type;     /* OG_TYPE_* */
+    int32_t dist;     /* OG_SYNTH_* */
+    uint32_t null_permille; /* 0 = no nulls */
+} og_synth_column;
+typedef struct og_synth_desc {
+    uint32_t n_series;
+    uint32_t rows_per_series;
+    uint32_t rows_per_segment; /* 1000 = lib/util/util.go:72 */
+    int64_t t0;                /* first timestamp */
+    int64_t dt;                /* cadence in ns (const-delta time pages) */
+    uint64_t seed;
+    uint32_t n_columns;
+    const og_synth_column *columns;
+} og_synth_desc;
+OG_API int og_shard_synth(const og_synth_desc *desc, og_shard **out);
+/* copy a shard's pages + directory back to host (for parity tests against the oracle): caller passes buffers
+ * sized from og_shard_info / og_shard_layout. */
+typedef struct og_shard_layout {
+    uint64_t data_len;
+    uint32_t n_series, n_segments, n_columns;
+} og_shard_layout;
+OG_API int og_shard_layout_get(const og_shard *s, og_shard_layout *out);
+OG_API int og_shard_export(const og_shard *s, uint8_t *data, uint64_t *sids, uint32_t *series_seg_begin,
+                           int64_t *seg_tmin, int64_t *seg_tmax, uint64_t *page_off /*[(n_columns+1)*n_segments], time last*/,
+                           uint32_t *page_len, int32_t *col_types /*[n_columns]*/);
+
+/* ---- re-encode (downsample / compaction): encode dense device columns into pages ---- */
+/* values: device [n_segments * rows_per_segment] 8-byte cells (bool: 1-byte cells), valid: device bitmap bytes per
+ * segment or NULL (no nulls); out pages are written back to back into d_out (capacity out_cap) and their offsets /
+ * lengths into d_page_off / d_page_len.  is_time selects EncodeTimestampBlock (chunkdata_builder.go:88-97). */
+OG_API int og_encode_pages(int32_t type, int32_t is_time, const void *d_values, const uint8_t *d_valid,
+                           const uint32_t *d_rows /*[n_segments] rows in each segment*/, uint32_t n_segments,
+                           uint32_t rows_per_segment, uint8_t *d_out, uint64_t out_cap, uint64_t *d_page_off,
+                           uint32_t *d_page_len, uint64_t *total_bytes_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGPU_H */
