@@ -88,6 +88,8 @@ enum { OG_GROUP_ALL = 0, OG_GROUP_PER_SERIES = 1, OG_GROUP_MAP = 2 };
 enum {
     OG_Q_STRICT_ORDER = 1u << 0 /* cross-series float sums in strict series order (bit-exact with the reference's
                                    sequential merge, lib/record/reccord_functions.go:730-733) instead of chunked order */
+    ,
+    OG_Q_NO_FUSED = 1u << 1 /* force the generic materialise-tile path even when the fused kernel is eligible (testing / A-B) */
 };
 
 typedef struct og_query_desc {

@@ -1,0 +1,9 @@
+"""opengemini_b200 — B200-native scan/aggregate path behind openGemini's cursor seam.
+
+Product = libogpu.so (hand-written sm_100a CUDA behind the C ABI in include/ogpu.h).
+This package only holds the host-side bindings; it never computes on the CPU.
+"""
+from . import _lib  # noqa: F401
+from .cursor import AggQuery, Shard  # noqa: F401
+
+__all__ = ["Shard", "AggQuery", "_lib"]

@@ -1,0 +1,730 @@
+/*
+ * api.cu — host side of libogpu.so: the C ABI declared in include/ogpu.h.
+ * No CPU compute path exists here: every entry point that produces data launches kernels or fails with OG_E_CUDA.
+ */
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "agg_kernels.cuh"
+#include "fused.cuh"
+#include "internal.h"
+
+namespace ogpu {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return OG_E_CUDA;
+}
+static int g_device = -1;
+
+static int map_dev_err(int code) {
+    switch (code) {
+    case D_UNSUPPORTED: return OG_E_UNSUPPORTED;
+    case D_TYPE: return OG_E_TYPE;
+    default: return OG_E_CORRUPT;
+    }
+}
+
+template <class T> static int dalloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? OG_E_NOMEM : OG_E_CUDA; }
+    return OG_OK;
+}
+
+static DirP make_dir(const og_shard *s) {
+    DirP d;
+    d.data = s->d_data; d.page_off = s->d_page_off; d.page_len = s->d_page_len; d.seg_series = s->d_seg_series;
+    d.seg_rows = s->d_seg_rows; d.series_seg_begin = s->d_series_seg_begin; d.seg_tmin = s->d_tmin; d.seg_tmax = s->d_tmax;
+    d.n_segments = s->n_segments; d.n_columns = s->n_columns;
+    return d;
+}
+
+/* derive seg_series / seg_rows / totals and validate codecs; shared by og_shard_open and og_shard_synth */
+int shard_finalize(og_shard *s) {
+    int rc;
+    if ((rc = dalloc(&s->d_seg_series, s->n_segments))) return rc;
+    if ((rc = dalloc(&s->d_seg_rows, s->n_segments))) return rc;
+    int32_t *d_types; unsigned long long *d_tot; uint32_t *d_max; int *d_err;
+    if ((rc = dalloc(&d_types, s->n_columns))) return rc;
+    if ((rc = dalloc(&d_tot, 2))) return rc;
+    if ((rc = dalloc(&d_max, 1))) return rc;
+    if ((rc = dalloc(&d_err, 2))) return rc;
+    CU(cudaMemcpy(d_types, s->col_types.data(), s->n_columns * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemset(d_tot, 0, 16)); CU(cudaMemset(d_max, 0, 4)); CU(cudaMemset(d_err, 0, 8));
+    if (s->n_series) k_fill_seg_series<<<s->n_series, 128>>>(s->d_series_seg_begin, s->n_series, s->d_seg_series);
+    if (s->n_segments) k_validate<<<(s->n_segments + 127) / 128, 128>>>(make_dir(s), d_types, s->d_seg_rows, d_tot, d_max, d_err);
+    CU(cudaGetLastError());
+    unsigned long long tot[2]; int err[2]; uint32_t mx;
+    CU(cudaMemcpy(tot, d_tot, 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&mx, d_max, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_types); cudaFree(d_tot); cudaFree(d_max); cudaFree(d_err);
+    if (err[0]) {
+        set_error("segment %d: %s page (device validation code %d)", err[1], err[0] == D_UNSUPPORTED ? "unsupported codec in" : err[0] == D_TYPE ? "type mismatch in" : "corrupt", err[0]);
+        return map_dev_err(err[0]);
+    }
+    s->n_rows = tot[0]; s->page_bytes = tot[1]; s->max_seg_rows = mx;
+    return OG_OK;
+}
+
+} // namespace ogpu
+
+using namespace ogpu;
+
+/* =============================================== lifecycle =============================================== */
+extern "C" {
+
+OG_API int og_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+OG_API int og_init(int device_ordinal) {
+    int n = og_device_count();
+    if (n <= 0) { set_error("no CUDA device visible: libogpu has no CPU path"); return OG_E_CUDA; }
+    if (device_ordinal < 0 || device_ordinal >= n) { set_error("device ordinal %d out of range (%d devices)", device_ordinal, n); return OG_E_INVAL; }
+    CU(cudaSetDevice(device_ordinal));
+    CU(cudaFree(0));
+    g_device = device_ordinal;
+    return OG_OK;
+}
+
+OG_API const char *og_strerror(int st) {
+    switch (st) {
+    case OG_OK: return "ok";
+    case OG_EOF: return "end of stream";
+    case OG_E_INVAL: return "invalid argument";
+    case OG_E_CUDA: return "CUDA failure or no device bound";
+    case OG_E_NOMEM: return "out of device memory";
+    case OG_E_UNSUPPORTED: return "unsupported codec or option on the GPU path";
+    case OG_E_CORRUPT: return "corrupt page";
+    case OG_E_ABORTED: return "query aborted";
+    case OG_E_TYPE: return "column type mismatch";
+    case OG_E_STATE: return "call sequence error";
+    default: return "unknown status";
+    }
+}
+OG_API const char *og_last_error(void) { return g_err; }
+OG_API const char *og_version(void) { return "ogpu 0.1 (sm_100a)"; }
+
+/* =============================================== shard =============================================== */
+} // extern "C"
+namespace ogpu {
+int ensure_device() {
+    if (g_device < 0) { int rc = og_init(0); if (rc != OG_OK) return rc; }
+    else CU(cudaSetDevice(g_device));
+    return OG_OK;
+}
+} // namespace ogpu
+static int need_device() { return ogpu::ensure_device(); }
+extern "C" {
+
+OG_API void og_shard_close(og_shard *s) {
+    if (!s) return;
+    if (s->owns_data && s->d_data) cudaFree(s->d_data);
+    cudaFree(s->d_series_seg_begin); cudaFree(s->d_seg_series); cudaFree(s->d_seg_rows); cudaFree(s->d_tmin); cudaFree(s->d_tmax);
+    cudaFree(s->d_page_off); cudaFree(s->d_page_len); cudaFree(s->d_sids);
+    if (s->h_seg_buf) cudaFreeHost(s->h_seg_buf);
+    if (s->d_seg_buf) cudaFree(s->d_seg_buf);
+    delete s;
+}
+
+OG_API int og_shard_open(const og_shard_desc *d, og_shard **out) {
+    if (!d || !out) { set_error("null argument"); return OG_E_INVAL; }
+    *out = nullptr;
+    int rc = need_device(); if (rc) return rc;
+    if (d->n_columns > 64 || (d->n_segments && (!d->seg_tmin || !d->seg_tmax || !d->time_page_off || !d->time_page_len)) || (d->n_series && !d->series_seg_begin)) { set_error("bad shard descriptor"); return OG_E_INVAL; }
+    for (uint32_t s = 0; s < d->n_series; s++) if (d->series_seg_begin[s] > d->series_seg_begin[s + 1]) { set_error("series_seg_begin not monotone at %u", s); return OG_E_INVAL; }
+    if (d->n_series && d->series_seg_begin[d->n_series] != d->n_segments) { set_error("series_seg_begin[n_series] != n_segments"); return OG_E_INVAL; }
+    og_shard *s = new og_shard;
+    s->device = g_device; s->n_series = d->n_series; s->n_segments = d->n_segments; s->n_columns = d->n_columns;
+    s->data_len = d->data_len;
+    for (uint32_t c = 0; c < d->n_columns; c++) {
+        s->col_types.push_back(d->columns[c].type);
+        s->col_names.push_back(d->columns[c].name ? d->columns[c].name : "");
+        if (d->columns[c].type != OG_TYPE_INT && d->columns[c].type != OG_TYPE_FLOAT && d->columns[c].type != OG_TYPE_BOOL) {
+            set_error("column %u: type %d is not decodable on the GPU path (strings are out of scope)", c, d->columns[c].type); delete s; return OG_E_UNSUPPORTED;
+        }
+    }
+    s->sids.assign(d->sids, d->sids + d->n_series);
+    s->h_series_seg_begin.assign(d->series_seg_begin, d->series_seg_begin + d->n_series + 1);
+    size_t nseg = d->n_segments, ncol1 = (size_t)d->n_columns + 1;
+    /* bounds + ordering checks on the host directory */
+    std::vector<uint64_t> off(ncol1 * nseg); std::vector<uint32_t> len(ncol1 * nseg);
+    for (size_t c = 0; c < ncol1; c++) {
+        const uint64_t *po = c < d->n_columns ? d->columns[c].page_off : d->time_page_off;
+        const uint32_t *pl = c < d->n_columns ? d->columns[c].page_len : d->time_page_len;
+        for (size_t g = 0; g < nseg; g++) {
+            if (po[g] + pl[g] > d->data_len) { set_error("column %zu segment %zu: page [%llu,+%u) outside data (%llu bytes)", c, g, (unsigned long long)po[g], pl[g], (unsigned long long)d->data_len); delete s; return OG_E_INVAL; }
+            off[c * nseg + g] = po[g]; len[c * nseg + g] = pl[g];
+        }
+    }
+    s->tmin = INT64_MAX; s->tmax = INT64_MIN;
+    for (uint32_t sr = 0; sr < d->n_series; sr++)
+        for (uint32_t g = d->series_seg_begin[sr]; g < d->series_seg_begin[sr + 1]; g++) {
+            if (d->seg_tmin[g] > d->seg_tmax[g] || (g > d->series_seg_begin[sr] && d->seg_tmin[g] <= d->seg_tmax[g - 1])) {
+                set_error("series %u: segment %u is not time-ordered (only ordered TSSP files are supported)", sr, g); delete s; return OG_E_UNSUPPORTED;
+            }
+            s->tmin = std::min(s->tmin, d->seg_tmin[g]); s->tmax = std::max(s->tmax, d->seg_tmax[g]);
+        }
+#define TRY(x) do { rc = (x); if (rc) { og_shard_close(s); return rc; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = cuda_fail(e_, #x, __FILE__, __LINE__); og_shard_close(s); return rc; } } while (0)
+    if (d->flags & OG_SHARD_DEVICE_DATA) { s->d_data = (uint8_t *)d->data; s->owns_data = false; }
+    else {
+        TRY(dalloc(&s->d_data, d->data_len + 32)); /* 16+ bytes of tail padding for the word-wise unaligned loads */
+        TRYCU(cudaMemcpy(s->d_data, d->data, d->data_len, cudaMemcpyHostToDevice));
+        TRYCU(cudaMemset(s->d_data + d->data_len, 0, 32));
+    }
+    TRY(dalloc(&s->d_series_seg_begin, (size_t)d->n_series + 1));
+    TRY(dalloc(&s->d_tmin, nseg)); TRY(dalloc(&s->d_tmax, nseg));
+    TRY(dalloc(&s->d_page_off, ncol1 * nseg)); TRY(dalloc(&s->d_page_len, ncol1 * nseg)); TRY(dalloc(&s->d_sids, (size_t)d->n_series));
+    TRYCU(cudaMemcpy(s->d_series_seg_begin, d->series_seg_begin, ((size_t)d->n_series + 1) * 4, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(s->d_tmin, d->seg_tmin, nseg * 8, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(s->d_tmax, d->seg_tmax, nseg * 8, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(s->d_page_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(s->d_page_len, len.data(), len.size() * 4, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(s->d_sids, d->sids, (size_t)d->n_series * 8, cudaMemcpyHostToDevice));
+    TRY(shard_finalize(s));
+    *out = s;
+    return OG_OK;
+}
+
+OG_API int og_shard_info(const og_shard *s, uint64_t *n_series, uint64_t *n_segments, uint64_t *n_rows, uint64_t *page_bytes, int64_t *tmin, int64_t *tmax) {
+    if (!s) return OG_E_INVAL;
+    if (n_series) *n_series = s->n_series;
+    if (n_segments) *n_segments = s->n_segments;
+    if (n_rows) *n_rows = s->n_rows;
+    if (page_bytes) *page_bytes = s->page_bytes;
+    if (tmin) *tmin = s->tmin;
+    if (tmax) *tmax = s->tmax;
+    return OG_OK;
+}
+
+OG_API int og_shard_layout_get(const og_shard *s, og_shard_layout *out) {
+    if (!s || !out) return OG_E_INVAL;
+    out->data_len = s->data_len; out->n_series = s->n_series; out->n_segments = s->n_segments; out->n_columns = s->n_columns;
+    return OG_OK;
+}
+
+OG_API int og_shard_export(const og_shard *s, uint8_t *data, uint64_t *sids, uint32_t *series_seg_begin, int64_t *seg_tmin,
+                           int64_t *seg_tmax, uint64_t *page_off, uint32_t *page_len, int32_t *col_types) {
+    if (!s) return OG_E_INVAL;
+    CU(cudaSetDevice(s->device));
+    size_t nseg = s->n_segments, ncol1 = (size_t)s->n_columns + 1;
+    if (data) CU(cudaMemcpy(data, s->d_data, s->data_len, cudaMemcpyDeviceToHost));
+    if (sids) memcpy(sids, s->sids.data(), s->sids.size() * 8);
+    if (series_seg_begin) memcpy(series_seg_begin, s->h_series_seg_begin.data(), s->h_series_seg_begin.size() * 4);
+    if (seg_tmin) CU(cudaMemcpy(seg_tmin, s->d_tmin, nseg * 8, cudaMemcpyDeviceToHost));
+    if (seg_tmax) CU(cudaMemcpy(seg_tmax, s->d_tmax, nseg * 8, cudaMemcpyDeviceToHost));
+    if (page_off) CU(cudaMemcpy(page_off, s->d_page_off, ncol1 * nseg * 8, cudaMemcpyDeviceToHost));
+    if (page_len) CU(cudaMemcpy(page_len, s->d_page_len, ncol1 * nseg * 4, cudaMemcpyDeviceToHost));
+    if (col_types) memcpy(col_types, s->col_types.data(), s->col_types.size() * 4);
+    return OG_OK;
+}
+
+/* =============================================== query =============================================== */
+static const int64_t MIN_TIME = INT64_MIN + 2, MAX_TIME = INT64_MAX - 1;
+/* ProcessorOptions.Window (lib/util/lifted/influx/query/select.go:579-655, Location == nil); host-side only:
+ * the kernels use the affine form start + b*interval that it implies for in-range rows. */
+static void window_of(int64_t interval, int64_t offset, int64_t tmin, int64_t tmax, int64_t t, int64_t *s, int64_t *e) {
+    if (interval == 0) { *s = tmin; *e = tmax + 1; return; }
+    t -= offset;
+    int64_t dt = t % interval;
+    if (dt < 0) dt += interval;
+    int64_t st = ((int64_t)((uint64_t)MIN_TIME + (uint64_t)dt) >= t) ? MIN_TIME : t - dt;
+    st += offset;
+    int64_t d2 = interval - dt;
+    int64_t en = (MAX_TIME - d2 <= t) ? MAX_TIME : t + d2;
+    en += offset;
+    *s = st; *e = en;
+}
+
+OG_API void og_query_destroy(og_query *q) {
+    if (!q) return;
+    for (void *p : q->scratch) cudaFree(p);
+    for (int c = 0; c < OG_MAX_CALLS; c++) { cudaFree(q->dense[c].val); cudaFree(q->dense[c].ok); cudaFree(q->dense[c].tim); }
+    cudaFree(q->d_group_of_series);
+    if (q->ev0) cudaEventDestroy(q->ev0);
+    if (q->ev1) cudaEventDestroy(q->ev1);
+    if (q->stream) cudaStreamDestroy(q->stream);
+    delete q;
+}
+
+OG_API int og_query_create(og_shard *s, const og_query_desc *d, og_query **out) {
+    if (!s || !d || !out) { set_error("null argument"); return OG_E_INVAL; }
+    *out = nullptr;
+    CU(cudaSetDevice(s->device));
+    if (!d->ascending) { set_error("descending scans are not supported on the GPU path"); return OG_E_UNSUPPORTED; }
+    if (d->n_calls == 0 || d->n_calls > OG_MAX_CALLS) { set_error("n_calls must be 1..%d", OG_MAX_CALLS); return OG_E_INVAL; }
+    if (d->n_filter > OG_MAX_FILTER) { set_error("filter too long (max %d items)", OG_MAX_FILTER); return OG_E_INVAL; }
+    if (d->interval < 0 || d->tmin > d->tmax) { set_error("bad interval or time range"); return OG_E_INVAL; }
+    og_query *q = new og_query;
+    q->sh = s; q->desc = *d;
+    q->calls.assign(d->calls, d->calls + d->n_calls);
+    if (d->n_filter) q->filter.assign(d->filter, d->filter + d->n_filter);
+    q->desc.calls = q->calls.data(); q->desc.filter = q->filter.data();
+    QueryP &p = q->qp;
+    memset(&p, 0, sizeof p);
+    /* column slots */
+    auto slot_of = [&](int col) -> int {
+        for (uint32_t i = 0; i < p.n_cols; i++) if (p.col_index[i] == col) return (int)i;
+        if (p.n_cols >= OG_MAX_COLS) return -1;
+        p.col_index[p.n_cols] = col; p.col_type[p.n_cols] = s->col_types[col];
+        return (int)p.n_cols++;
+    };
+    for (uint32_t i = 0; i < d->n_calls; i++) {
+        const og_call &c = d->calls[i];
+        if (c.column < 0 || (uint32_t)c.column >= s->n_columns || c.func < OG_AGG_COUNT || c.func > OG_AGG_LAST) { set_error("call %u: bad column or function", i); delete q; return OG_E_INVAL; }
+        int type = s->col_types[c.column];
+        if (c.func == OG_AGG_SUM && type == OG_TYPE_BOOL) { set_error("sum() over a boolean column (unsupported sum iterator type, series_call_processor.go:140)"); delete q; return OG_E_INVAL; }
+        int sl = slot_of(c.column);
+        if (sl < 0) { set_error("too many distinct columns"); delete q; return OG_E_INVAL; }
+        p.calls[i].func = c.func; p.calls[i].col_slot = sl; p.calls[i].type = type;
+        p.calls[i].out_type = c.func == OG_AGG_COUNT ? OG_TYPE_INT : type;
+    }
+    p.n_calls = d->n_calls; p.multi = d->n_calls > 1;
+    int sp = 0;
+    for (uint32_t i = 0; i < d->n_filter; i++) {
+        const og_filter_item &f = d->filter[i];
+        FilterP &fp = p.filter[i];
+        fp.kind = f.kind;
+        if (f.kind == OG_F_TERM) {
+            if (f.column < 0 || (uint32_t)f.column >= s->n_columns || f.op < OG_OP_LT || f.op > OG_OP_NEQ) { set_error("filter item %u: bad column or op", i); delete q; return OG_E_INVAL; }
+            int sl = slot_of(f.column);
+            if (sl < 0) { set_error("too many distinct columns"); delete q; return OG_E_INVAL; }
+            fp.col_slot = sl; fp.op = f.op; fp.type = s->col_types[f.column]; fp.const_is_float = f.const_is_float; fp.fval = f.fval; fp.ival = f.ival;
+            sp++;
+        } else if (f.kind == OG_F_AND || f.kind == OG_F_OR) {
+            if (sp < 2) { set_error("filter RPN underflow at item %u", i); delete q; return OG_E_INVAL; }
+            sp--;
+        } else { set_error("filter item %u: bad kind", i); delete q; return OG_E_INVAL; }
+    }
+    if (d->n_filter && sp != 1) { set_error("filter RPN does not reduce to one value"); delete q; return OG_E_INVAL; }
+    p.n_filter = d->n_filter;
+    /* bucket geometry: TimeWindowsInit (agg_tagset_cursor.go:1012-1027) over the query range (updateQueryTime :448-463) */
+    int64_t s0, e0, s1, e1;
+    window_of(d->interval, d->offset, d->tmin, d->tmax, d->tmin, &s0, &e0);
+    window_of(d->interval, d->offset, d->tmin, d->tmax, d->tmax + 1, &s1, &e1);
+    p.tmin = d->tmin; p.tmax = d->tmax; p.start = s0; p.interval = e0 - s0;
+    if (p.interval <= 0) { set_error("degenerate window"); delete q; return OG_E_INVAL; }
+    uint64_t nb = d->interval ? (uint64_t)(e1 - s0) / (uint64_t)p.interval : 1;
+    if (nb == 0 || nb > 0x7fffffffull) { set_error("query range yields %llu buckets", (unsigned long long)nb); delete q; return OG_E_INVAL; }
+    p.n_buckets = (uint32_t)nb;
+    /* groups */
+    q->n_groups = d->group_mode == OG_GROUP_ALL ? 1 : d->group_mode == OG_GROUP_PER_SERIES ? s->n_series : d->n_groups;
+    if (d->group_mode == OG_GROUP_MAP) {
+        if (!d->series_group || d->n_groups == 0) { set_error("OG_GROUP_MAP needs series_group and n_groups"); delete q; return OG_E_INVAL; }
+        q->series_group.assign(d->series_group, d->series_group + s->n_series);
+        for (uint32_t g : q->series_group) if (g >= d->n_groups) { set_error("series_group entry out of range"); delete q; return OG_E_INVAL; }
+    } else if (d->group_mode != OG_GROUP_ALL && d->group_mode != OG_GROUP_PER_SERIES) { set_error("bad group_mode"); delete q; return OG_E_INVAL; }
+    if (q->n_groups == 0) q->n_groups = 1;
+    cudaError_t e = cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete q; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    cudaEventCreate(&q->ev0); cudaEventCreate(&q->ev1);
+    *out = q;
+    return OG_OK;
+}
+
+OG_API void og_query_abort(og_query *q) { if (q) q->aborted = 1; }
+
+} /* extern "C" */
+namespace {
+struct ScratchSet { std::vector<void *> ptrs; ~ScratchSet() { for (void *p : ptrs) cudaFree(p); } };
+template <class T> int salloc(ScratchSet &ss, T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) ss.ptrs.push_back(*p); return rc; }
+
+template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP &ch, cudaStream_t st) {
+    uint32_t n = ch.seg_end - ch.seg_begin;
+    k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch);
+}
+} // namespace
+extern "C" {
+
+OG_API int og_query_run(og_query *q) {
+    if (!q) return OG_E_INVAL;
+    og_shard *s = q->sh;
+    CU(cudaSetDevice(s->device));
+    const QueryP &p = q->qp;
+    cudaStream_t st = q->stream;
+    int rc;
+    q->host_ready = false; q->next_group = 0; q->next_row = 0;
+    size_t cells_dense = (size_t)q->n_groups * p.n_buckets;
+    /* dense accumulators */
+    for (uint32_t c = 0; c < p.n_calls; c++) {
+        bool sel = p.calls[c].func >= OG_AGG_MIN && !(p.multi && p.calls[c].func <= OG_AGG_MAX);
+        if (!q->dense[c].val) {
+            if ((rc = dalloc(&q->dense[c].val, cells_dense))) return rc;
+            if ((rc = dalloc(&q->dense[c].ok, cells_dense))) return rc;
+            if (sel && (rc = dalloc(&q->dense[c].tim, cells_dense))) return rc;
+        }
+    }
+    ScratchSet ss;
+    /* group CSR */
+    std::vector<uint32_t> grp_begin(q->n_groups + 1, 0), grp_series(s->n_series);
+    if (q->desc.group_mode == OG_GROUP_MAP) {
+        for (uint32_t sr = 0; sr < s->n_series; sr++) grp_begin[q->series_group[sr] + 1]++;
+        for (uint32_t g = 0; g < q->n_groups; g++) grp_begin[g + 1] += grp_begin[g];
+        std::vector<uint32_t> cur(grp_begin.begin(), grp_begin.end() - 1);
+        for (uint32_t sr = 0; sr < s->n_series; sr++) grp_series[cur[q->series_group[sr]]++] = sr;
+    } else if (q->desc.group_mode == OG_GROUP_PER_SERIES) {
+        for (uint32_t g = 0; g <= q->n_groups; g++) grp_begin[g] = std::min(g, s->n_series);
+        std::iota(grp_series.begin(), grp_series.end(), 0u);
+    } else { grp_begin[1] = s->n_series; std::iota(grp_series.begin(), grp_series.end(), 0u); }
+    uint32_t *d_grp_begin, *d_grp_series; int *d_err;
+    if ((rc = salloc(ss, &d_grp_begin, grp_begin.size()))) return rc;
+    if ((rc = salloc(ss, &d_grp_series, grp_series.size()))) return rc;
+    if ((rc = salloc(ss, &d_err, 2))) return rc;
+    CU(cudaMemcpyAsync(d_grp_begin, grp_begin.data(), grp_begin.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_grp_series, grp_series.data(), grp_series.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_err, 0, 8, st));
+    GroupP gp; memset(&gp, 0, sizeof gp);
+    gp.grp_begin = d_grp_begin; gp.grp_series = d_grp_series; gp.n_groups = q->n_groups;
+    for (uint32_t c = 0; c < p.n_calls; c++) gp.dense[c] = q->dense[c];
+
+    /* chunk plan: whole series, cells budget */
+    size_t cell_bytes_per_series = 0;
+    for (uint32_t c = 0; c < p.n_calls; c++) cell_bytes_per_series += (size_t)p.n_buckets * (9 + (p.calls[c].func >= OG_AGG_MIN ? 8 : 0));
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
+    uint32_t chunk_series = (uint32_t)std::max<size_t>(1, std::min<size_t>(s->n_series, budget / std::max<size_t>(1, cell_bytes_per_series)));
+    /* widest chunk in segments, for the edge arrays */
+    uint32_t max_chunk_segs = 0;
+    for (uint32_t a = 0; a < s->n_series; a += chunk_series) {
+        uint32_t b = std::min(s->n_series, a + chunk_series);
+        max_chunk_segs = std::max(max_chunk_segs, s->h_series_seg_begin[b] - s->h_series_seg_begin[a]);
+    }
+    ChunkP ch; memset(&ch, 0, sizeof ch);
+    ch.err = d_err;
+    size_t chunk_cells = (size_t)chunk_series * p.n_buckets;
+    for (uint32_t c = 0; c < p.n_calls; c++) {
+        bool sel = p.calls[c].func >= OG_AGG_MIN;
+        if ((rc = salloc(ss, &ch.cells[c].val, chunk_cells))) return rc;
+        if ((rc = salloc(ss, &ch.cells[c].ok, chunk_cells))) return rc;
+        if (sel && (rc = salloc(ss, &ch.cells[c].tim, chunk_cells))) return rc;
+        if ((rc = salloc(ss, &ch.edges[c].val, 2 * (size_t)max_chunk_segs))) return rc;
+        if ((rc = salloc(ss, &ch.edges[c].ok, 2 * (size_t)max_chunk_segs))) return rc;
+        if (sel && (rc = salloc(ss, &ch.edges[c].tim, 2 * (size_t)max_chunk_segs))) return rc;
+    }
+    if ((rc = salloc(ss, &ch.edge_bucket, 2 * (size_t)max_chunk_segs))) return rc;
+
+    bool fused = p.n_cols == 1 && p.n_filter == 0 && !(q->desc.flags & OG_Q_NO_FUSED);
+    q->path_used = fused ? 1 : 0;
+    /* generic path tile buffers */
+    TileP tp; memset(&tp, 0, sizeof tp);
+    uint32_t tile_segs = 0;
+    if (!fused) {
+        tp.R = std::max<uint32_t>(1, s->max_seg_rows);
+        size_t per_seg = (size_t)tp.R * (p.n_cols * 9 + 8 + 1);
+        tile_segs = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max<uint32_t>(1, max_chunk_segs), ((size_t)96 << 20) / per_seg));
+        for (uint32_t k = 0; k < p.n_cols; k++) {
+            if ((rc = salloc(ss, &tp.vals[k], (size_t)tile_segs * tp.R))) return rc;
+            if ((rc = salloc(ss, &tp.okb[k], (size_t)tile_segs * tp.R))) return rc;
+        }
+        if ((rc = salloc(ss, &tp.times, (size_t)tile_segs * tp.R))) return rc;
+        if ((rc = salloc(ss, &tp.keep, (size_t)tile_segs * tp.R))) return rc;
+    }
+    DirP dir = make_dir(s);
+    uint32_t launches = 0;
+    CU(cudaEventRecord(q->ev0, st));
+    k_init_dense<<<(unsigned)((cells_dense + 255) / 256), 256, 0, st>>>(p, gp); launches++;
+    uint64_t segs_scanned = 0;
+    for (uint32_t a = 0; a < s->n_series; a += chunk_series) {
+        if (q->aborted) { cudaStreamSynchronize(st); set_error("query aborted"); return OG_E_ABORTED; }
+        uint32_t b = std::min(s->n_series, a + chunk_series);
+        ch.series_begin = a; ch.series_end = b;
+        ch.seg_begin = s->h_series_seg_begin[a]; ch.seg_end = s->h_series_seg_begin[b];
+        uint32_t nseg = ch.seg_end - ch.seg_begin;
+        if (nseg == 0) continue;
+        segs_scanned += nseg;
+        for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)(b - a) * p.n_buckets, st));
+        if (fused) {
+            switch (p.n_calls) {
+            case 1: launch_fused<1>(dir, p, ch, st); break;
+            case 2: launch_fused<2>(dir, p, ch, st); break;
+            case 3: launch_fused<3>(dir, p, ch, st); break;
+            case 4: launch_fused<4>(dir, p, ch, st); break;
+            case 5: launch_fused<5>(dir, p, ch, st); break;
+            case 6: launch_fused<6>(dir, p, ch, st); break;
+            case 7: launch_fused<7>(dir, p, ch, st); break;
+            default: launch_fused<8>(dir, p, ch, st); break;
+            }
+            launches++;
+        } else {
+            for (uint32_t t0 = ch.seg_begin; t0 < ch.seg_end; t0 += tile_segs) {
+                tp.tile_begin = t0; tp.tile_end = std::min(ch.seg_end, t0 + tile_segs);
+                uint32_t n = tp.tile_end - tp.tile_begin;
+                dim3 g((n + 127) / 128, p.n_cols + 1);
+                k_decode_tile<<<g, 128, 0, st>>>(dir, p, tp, d_err);
+                size_t rows_total = (size_t)n * tp.R;
+                k_filter_tile<<<(unsigned)((rows_total + 255) / 256), 256, 0, st>>>(dir, p, tp);
+                k_window_reduce<<<(n * 32 + 127) / 128, 128, 0, st>>>(dir, p, tp, ch);
+                launches += 3;
+            }
+        }
+        k_fix_edges<<<(nseg + 127) / 128, 128, 0, st>>>(dir, p, ch);
+        k_merge_groups<<<(unsigned)((cells_dense + 127) / 128), 128, 0, st>>>(p, ch, gp);
+        launches += 2;
+    }
+    CU(cudaEventRecord(q->ev1, st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    int err[2];
+    CU(cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost));
+    if (err[0]) { set_error("segment %d failed to decode (device code %d)", err[1], err[0]); return map_dev_err(err[0]); }
+    float ms = 0; cudaEventElapsedTime(&ms, q->ev0, q->ev1);
+    og_stats &stt = q->stats;
+    memset(&stt, 0, sizeof stt);
+    stt.kernel_ms = ms; stt.kernel_launches = launches; stt.segments_scanned = segs_scanned;
+    stt.rows_decoded = s->n_rows; /* every segment overlapping the range is decoded whole; pruned segments are counted out below */
+    /* page bytes of the columns this query touched + time pages */
+    stt.page_bytes = 0; /* filled lazily by og_query_stats from the directory (kept off the timed path) */
+    stt.dir_bytes = (uint64_t)s->n_segments * (8 + 4) * (p.n_cols + 1) + (uint64_t)s->n_segments * (4 + 4 + 16);
+    stt.out_bytes = 0;
+    for (uint32_t c = 0; c < p.n_calls; c++) stt.out_bytes += cells_dense * (9 + (q->dense[c].tim ? 8 : 0));
+    q->ran = true;
+    return OG_OK;
+}
+
+OG_API int og_query_dense(og_query *q, og_dense_view *out) {
+    if (!q || !out) return OG_E_INVAL;
+    if (!q->ran) { set_error("og_query_dense before og_query_run"); return OG_E_STATE; }
+    const QueryP &p = q->qp;
+    out->n_groups = q->n_groups; out->n_buckets = p.n_buckets; out->start = p.start; out->interval = q->desc.interval ? p.interval : 0;
+    out->n_cols = p.n_calls;
+    for (uint32_t c = 0; c < p.n_calls; c++) {
+        q->dense_cols[c].values = q->dense[c].val; q->dense_cols[c].valid = q->dense[c].ok; q->dense_cols[c].times = q->dense[c].tim;
+        q->dense_cols[c].type = p.calls[c].out_type; q->dense_cols[c].func = p.calls[c].func;
+    }
+    out->cols = q->dense_cols; out->stream = q->stream;
+    return OG_OK;
+}
+
+} /* extern "C" */
+namespace {
+__global__ void k_sum_page_bytes(DirP d, QueryP q, int64_t tmin, int64_t tmax, unsigned long long *out /*[0] bytes [1] rows [2] segs*/) {
+    uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= d.n_segments) return;
+    if (d.seg_tmax[seg] < tmin || d.seg_tmin[seg] > tmax) return;
+    unsigned long long b = d.page_len[(size_t)d.n_columns * d.n_segments + seg];
+    for (uint32_t k = 0; k < q.n_cols; k++) b += d.page_len[(size_t)q.col_index[k] * d.n_segments + seg];
+    atomicAdd(&out[0], b); atomicAdd(&out[1], (unsigned long long)d.seg_rows[seg]); atomicAdd(&out[2], 1ull);
+}
+} // namespace
+extern "C" {
+
+OG_API int og_query_stats(const og_query *q, og_stats *out) {
+    if (!q || !out) return OG_E_INVAL;
+    og_query *mq = const_cast<og_query *>(q);
+    if (q->ran && q->stats.page_bytes == 0) {
+        CU(cudaSetDevice(q->sh->device));
+        unsigned long long *d_o; int rc = dalloc(&d_o, 3); if (rc) return rc;
+        cudaMemset(d_o, 0, 24);
+        if (q->sh->n_segments) k_sum_page_bytes<<<(q->sh->n_segments + 255) / 256, 256>>>(make_dir(q->sh), q->qp, q->qp.tmin, q->qp.tmax, d_o);
+        unsigned long long h[3]; CU(cudaMemcpy(h, d_o, 24, cudaMemcpyDeviceToHost)); cudaFree(d_o);
+        mq->stats.page_bytes = h[0]; mq->stats.rows_decoded = h[1]; mq->stats.segments_scanned = h[2];
+    }
+    *out = q->stats;
+    return OG_OK;
+}
+
+OG_API int og_query_merge_dense(og_query *q, const og_dense_view *other) {
+    if (!q || !other) return OG_E_INVAL;
+    if (!q->ran) return OG_E_STATE;
+    const QueryP &p = q->qp;
+    if (other->n_groups != q->n_groups || other->n_buckets != p.n_buckets || other->n_cols != p.n_calls) { set_error("dense shapes differ"); return OG_E_INVAL; }
+    CU(cudaSetDevice(q->sh->device));
+    GroupP mine, oth; memset(&mine, 0, sizeof mine); memset(&oth, 0, sizeof oth);
+    mine.n_groups = oth.n_groups = q->n_groups;
+    for (uint32_t c = 0; c < p.n_calls; c++) {
+        mine.dense[c] = q->dense[c];
+        oth.dense[c].val = (uint64_t *)other->cols[c].values; oth.dense[c].ok = other->cols[c].valid; oth.dense[c].tim = other->cols[c].times;
+        if ((q->dense[c].tim != nullptr) != (oth.dense[c].tim != nullptr)) { set_error("dense column %u: times presence differs", c); return OG_E_INVAL; }
+    }
+    size_t total = (size_t)q->n_groups * p.n_buckets;
+    k_merge_dense<<<(unsigned)((total + 255) / 256), 256, 0, q->stream>>>(p, mine, oth);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(q->stream));
+    q->host_ready = false;
+    return OG_OK;
+}
+
+/* KeyCursor.Next: TransIntervalRec2Rec (lib/record/record.go:1340-1358) in slices of ChunkSizeNum (agg_tagset_cursor.go:993-1006) */
+OG_API int og_query_next(og_query *q, og_record_view *out) {
+    if (!q || !out) return OG_E_INVAL;
+    if (!q->ran) { set_error("og_query_next before og_query_run"); return OG_E_STATE; }
+    if (q->aborted) return OG_E_ABORTED;
+    const QueryP &p = q->qp;
+    size_t total = (size_t)q->n_groups * p.n_buckets;
+    if (!q->host_ready) {
+        CU(cudaSetDevice(q->sh->device));
+        for (uint32_t c = 0; c < p.n_calls; c++) {
+            q->h_val[c].resize(total); q->h_ok[c].resize(total);
+            CU(cudaMemcpy(q->h_val[c].data(), q->dense[c].val, total * 8, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(q->h_ok[c].data(), q->dense[c].ok, total, cudaMemcpyDeviceToHost));
+            if (q->dense[c].tim) { q->h_tim[c].resize(total); CU(cudaMemcpy(q->h_tim[c].data(), q->dense[c].tim, total * 8, cudaMemcpyDeviceToHost)); }
+        }
+        q->host_ready = true; q->next_group = 0; q->next_row = 0;
+    }
+    int chunk = q->desc.chunk_size > 0 ? q->desc.chunk_size : 1024;
+    uint32_t nc = p.n_calls;
+    q->rv_val.assign(nc, {}); q->rv_bitmap.assign(nc, {}); q->rv_coltimes.assign(nc, {}); q->rv_times.clear(); q->rv_cols.assign(nc, og_colval_view{});
+    while (q->next_group < q->n_groups) {
+        uint32_t g = q->next_group;
+        std::vector<int32_t> nil(nc, 0);
+        int rows = 0;
+        uint32_t b = q->next_row;
+        /* a slice covers `chunk` interval rows; empty rows inside it are dropped */
+        uint32_t b_end = (uint32_t)std::min<uint64_t>(p.n_buckets, (uint64_t)b + (uint64_t)chunk);
+        for (; b < b_end; b++) {
+            size_t i = (size_t)g * p.n_buckets + b;
+            bool any = false;
+            for (uint32_t c = 0; c < nc; c++) any |= q->h_ok[c][i] != 0;
+            if (!any) continue;
+            int64_t row_time = p.start + (int64_t)b * p.interval;
+            if (q->desc.interval == 0) row_time = 0;
+            for (uint32_t c = 0; c < nc; c++) {
+                bool ok = q->h_ok[c][i] != 0;
+                if ((size_t)(rows >> 3) >= q->rv_bitmap[c].size()) q->rv_bitmap[c].push_back(0);
+                if (ok) {
+                    q->rv_bitmap[c][rows >> 3] |= (uint8_t)(1 << (rows & 7));
+                    if (p.calls[c].out_type == OG_TYPE_BOOL) q->rv_val[c].push_back((uint8_t)(q->h_val[c][i] != 0));
+                    else { const uint8_t *pv = (const uint8_t *)&q->h_val[c][i]; q->rv_val[c].insert(q->rv_val[c].end(), pv, pv + 8); }
+                } else nil[c]++;
+                if (q->dense[c].tim) {
+                    if (p.multi) q->rv_coltimes[c].push_back(ok ? q->h_tim[c][i] : 0);
+                    else if (ok) row_time = q->h_tim[c][i]; /* single-call selector: the row carries the point's time */
+                }
+            }
+            q->rv_times.push_back(row_time);
+            rows++;
+        }
+        q->next_row = b_end;
+        if (q->next_row >= p.n_buckets) { q->next_group++; q->next_row = 0; }
+        if (rows == 0) continue;
+        for (uint32_t c = 0; c < nc; c++) {
+            og_colval_view &v = q->rv_cols[c];
+            v.val = q->rv_val[c].data(); v.val_bytes = q->rv_val[c].size(); v.bitmap = q->rv_bitmap[c].data();
+            v.times = (p.multi && q->dense[c].tim) ? q->rv_coltimes[c].data() : nullptr;
+            v.type = p.calls[c].out_type; v.len = rows; v.nil_count = nil[c]; v.bitmap_offset = 0;
+        }
+        out->n_cols = nc; out->cols = q->rv_cols.data(); out->times = q->rv_times.data(); out->rows = rows; out->group = g;
+        out->sid = q->desc.group_mode == OG_GROUP_PER_SERIES ? q->sh->sids[g] : 0;
+        return OG_OK;
+    }
+    return OG_EOF;
+}
+
+/* =============================================== materialise path =============================================== */
+} /* extern "C" */
+namespace {
+struct DenseEmit { uint8_t *out; int wide; __device__ __forceinline__ void operator()(uint32_t i, uint64_t bits) { if (wide) ((uint64_t *)out)[i] = bits; else out[i] = (uint8_t)bits; } };
+
+/* decode [seg_begin, seg_end) of one column into dense non-null values (ColVal.Val layout, reader.go:504-579) */
+__global__ void k_decode_column(DirP d, uint32_t column, int type, uint32_t seg_begin, uint32_t seg_end, uint8_t *out, uint64_t stride,
+                                uint32_t *rows_out, uint8_t *bitmap_out, uint32_t bitmap_stride, int *err) {
+    uint32_t seg = seg_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= seg_end) return;
+    uint8_t *o = out + (size_t)(seg - seg_begin) * stride;
+    uint32_t rows = d.seg_rows[seg];
+    size_t pi = (size_t)column * d.n_segments + seg;
+    if (column == d.n_columns) { /* time column */
+        TimeDesc t;
+        int rc = parse_time_page(d.data + d.page_off[pi], d.page_len[pi], t);
+        if (rc == D_OK) { TimeStore ts{(int64_t *)o}; rc = decode_time_values(t, ts); }
+        if (rc != D_OK) report_err(err, rc, seg);
+        if (rows_out) rows_out[seg - seg_begin] = rows;
+        return;
+    }
+    uint32_t len = d.page_len[pi];
+    uint8_t *bm = bitmap_out ? bitmap_out + (size_t)(seg - seg_begin) * bitmap_stride : nullptr;
+    if (len == 0) {
+        if (rows_out) rows_out[seg - seg_begin] = 0;
+        if (bm) for (uint32_t i = 0; i < (rows + 7) / 8; i++) bm[i] = 0;
+        return;
+    }
+    PageHdr h;
+    int rc = parse_field_header(d.data + d.page_off[pi], len, type, rows, h);
+    if (rc == D_OK) {
+        DenseEmit em{o, type != OG_TYPE_BOOL};
+        rc = decode_block(type, h, em);
+        if (rows_out) rows_out[seg - seg_begin] = h.rows - h.nil_count;
+        if (bm) { /* AppendBitmap re-packed at offset 0 (lib/record/column.go:79-112) */
+            for (uint32_t i = 0; i < (rows + 7) / 8; i++) {
+                uint8_t v = 0;
+                for (uint32_t k = 0; k < 8 && i * 8 + k < rows; k++) v |= (uint8_t)(hdr_row_valid(h, i * 8 + k) ? 1 : 0) << k;
+                bm[i] = v;
+            }
+        }
+    }
+    if (rc != D_OK) report_err(err, rc, seg);
+}
+} // namespace
+extern "C" {
+
+OG_API int og_decode_column_device(og_shard *s, uint32_t column, uint32_t seg_begin, uint32_t seg_end, void *d_values,
+                                   uint64_t value_stride_bytes, uint32_t *d_rows_out) {
+    if (!s || !d_values || column > s->n_columns || seg_begin > seg_end || seg_end > s->n_segments) { set_error("bad argument"); return OG_E_INVAL; }
+    CU(cudaSetDevice(s->device));
+    if (seg_begin == seg_end) return OG_OK;
+    int *d_err; int rc = dalloc(&d_err, 2); if (rc) return rc;
+    cudaMemset(d_err, 0, 8);
+    int type = column == s->n_columns ? OG_TYPE_INT : s->col_types[column];
+    uint32_t n = seg_end - seg_begin;
+    k_decode_column<<<(n + 127) / 128, 128>>>(make_dir(s), column, type, seg_begin, seg_end, (uint8_t *)d_values, value_stride_bytes, d_rows_out, nullptr, 0, d_err);
+    int err[2]; cudaError_t e = cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost); cudaFree(d_err);
+    if (e != cudaSuccess) return cuda_fail(e, "k_decode_column", __FILE__, __LINE__);
+    if (err[0]) { set_error("segment %d failed to decode (device code %d)", err[1], err[0]); return map_dev_err(err[0]); }
+    return OG_OK;
+}
+
+/* one segment -> Record view in pinned host memory (the KeyCursor.Next of a non-aggregating reader) */
+OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out) {
+    if (!s || !out || segment >= s->n_segments) { set_error("bad argument"); return OG_E_INVAL; }
+    CU(cudaSetDevice(s->device));
+    uint32_t R = std::max<uint32_t>(1, s->max_seg_rows);
+    size_t ncol1 = (size_t)s->n_columns + 1;
+    size_t val_stride = (size_t)R * 8, bm_stride = (R + 7) / 8;
+    size_t need = ncol1 * (val_stride + bm_stride + 16);
+    if (s->d_seg_buf_bytes < need) {
+        if (s->d_seg_buf) cudaFree(s->d_seg_buf);
+        if (s->h_seg_buf) cudaFreeHost(s->h_seg_buf);
+        CU(cudaMalloc(&s->d_seg_buf, need)); CU(cudaMallocHost(&s->h_seg_buf, need));
+        s->d_seg_buf_bytes = s->h_seg_buf_bytes = need;
+    }
+    uint8_t *dv = (uint8_t *)s->d_seg_buf, *dbm = dv + ncol1 * val_stride;
+    uint32_t *drows = (uint32_t *)(dbm + ncol1 * bm_stride);
+    int *d_err; int rc = dalloc(&d_err, 2); if (rc) return rc;
+    cudaMemset(d_err, 0, 8);
+    DirP dir = make_dir(s);
+    for (uint32_t c = 0; c <= s->n_columns; c++) {
+        int type = c == s->n_columns ? OG_TYPE_INT : s->col_types[c];
+        k_decode_column<<<1, 32>>>(dir, c, type, segment, segment + 1, dv + c * val_stride, val_stride, drows + c, dbm + c * bm_stride, (uint32_t)bm_stride, d_err);
+    }
+    int err[2]; cudaError_t e = cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost); cudaFree(d_err);
+    if (e != cudaSuccess) return cuda_fail(e, "k_decode_column", __FILE__, __LINE__);
+    if (err[0]) { set_error("segment %d failed to decode (device code %d)", err[1], err[0]); return map_dev_err(err[0]); }
+    CU(cudaMemcpy(s->h_seg_buf, s->d_seg_buf, need, cudaMemcpyDeviceToHost));
+    uint8_t *hv = (uint8_t *)s->h_seg_buf, *hbm = hv + ncol1 * val_stride;
+    uint32_t *hrows = (uint32_t *)(hbm + ncol1 * bm_stride);
+    uint32_t rows = hrows[s->n_columns];
+    s->seg_views.assign(s->n_columns, og_colval_view{});
+    for (uint32_t c = 0; c < s->n_columns; c++) {
+        og_colval_view &v = s->seg_views[c];
+        uint32_t nv = hrows[c];
+        v.val = hv + c * val_stride; v.val_bytes = (uint64_t)nv * (s->col_types[c] == OG_TYPE_BOOL ? 1 : 8);
+        v.bitmap = hbm + c * bm_stride; v.times = nullptr; v.type = s->col_types[c]; v.len = (int32_t)rows; v.nil_count = (int32_t)(rows - nv); v.bitmap_offset = 0;
+    }
+    out->n_cols = s->n_columns; out->cols = s->seg_views.data(); out->times = (const int64_t *)(hv + s->n_columns * val_stride); out->rows = (int32_t)rows; out->group = 0;
+    /* series id of the segment */
+    uint32_t sr = (uint32_t)(std::upper_bound(s->h_series_seg_begin.begin(), s->h_series_seg_begin.end(), segment) - s->h_series_seg_begin.begin()) - 1;
+    out->sid = s->sids[sr];
+    return OG_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,105 @@
+/*
+ * internal.h — host-side handle layouts and kernel parameter blocks shared by the .cu files of libogpu.so.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/ogpu.h"
+
+#define OG_MAX_CALLS 8
+#define OG_MAX_FILTER 16
+#define OG_MAX_COLS 8 /* distinct field columns one query may touch */
+
+namespace ogpu {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ::ogpu::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
+
+struct DevBuf { /* RAII-less helper: explicit free */
+    void *p = nullptr; size_t bytes = 0;
+};
+
+} // namespace ogpu
+
+struct og_shard {
+    int device = 0;
+    uint8_t *d_data = nullptr; uint64_t data_len = 0; bool owns_data = true;
+    uint32_t n_series = 0, n_segments = 0, n_columns = 0;
+    uint32_t max_seg_rows = 0;
+    uint64_t n_rows = 0, page_bytes = 0;
+    int64_t tmin = 0, tmax = 0;
+    std::vector<uint64_t> sids;
+    std::vector<int32_t> col_types;
+    std::vector<std::string> col_names;
+    std::vector<uint32_t> h_series_seg_begin; /* always mirrored on host (n_series+1) */
+    /* device directory (SoA) */
+    uint32_t *d_series_seg_begin = nullptr; /* [n_series+1] */
+    uint32_t *d_seg_series = nullptr;       /* [n_segments] */
+    uint32_t *d_seg_rows = nullptr;         /* [n_segments] rows per segment (from the time page) */
+    int64_t *d_tmin = nullptr, *d_tmax = nullptr; /* [n_segments] */
+    uint64_t *d_page_off = nullptr;         /* [(n_columns+1) * n_segments], time column last */
+    uint32_t *d_page_len = nullptr;
+    uint64_t *d_sids = nullptr;
+    /* materialise scratch for og_decode_segment (host pinned + device) */
+    void *h_seg_buf = nullptr; size_t h_seg_buf_bytes = 0;
+    void *d_seg_buf = nullptr; size_t d_seg_buf_bytes = 0;
+    std::vector<og_colval_view> seg_views;
+};
+
+namespace ogpu {
+
+struct CallP { int32_t func, col_slot, type, out_type; };
+struct FilterP { int32_t kind, col_slot, op, type, const_is_float; double fval; int64_t ival; };
+
+/* per-call cell/edge/dense array triple */
+struct Tri { uint64_t *val; int64_t *tim; uint8_t *ok; };
+
+struct QueryP { /* passed by value to kernels */
+    int64_t tmin, tmax, start, interval; /* interval = window length (end-start of Window()); >0 always on device */
+    uint32_t n_buckets, n_calls, n_filter, n_cols;
+    int32_t multi; /* callCount > 1 */
+    CallP calls[OG_MAX_CALLS];
+    FilterP filter[OG_MAX_FILTER];
+    int32_t col_index[OG_MAX_COLS]; /* shard column of each slot */
+    int32_t col_type[OG_MAX_COLS];
+};
+
+} // namespace ogpu
+
+struct og_query {
+    og_shard *sh = nullptr;
+    og_query_desc desc{};
+    std::vector<og_call> calls;
+    std::vector<og_filter_item> filter;
+    std::vector<uint32_t> series_group;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ogpu::QueryP qp{};
+    uint32_t n_groups = 0;
+    bool ran = false; volatile int aborted = 0;
+    /* dense result */
+    ogpu::Tri dense[OG_MAX_CALLS]{};
+    og_dense_col dense_cols[OG_MAX_CALLS]{};
+    /* group membership CSR on device (series sorted by group, stable) */
+    uint32_t *d_group_of_series = nullptr; /* [n_series] */
+    /* scratch */
+    std::vector<void *> scratch;
+    og_stats stats{};
+    /* host staging for og_query_next */
+    std::vector<uint64_t> h_val[OG_MAX_CALLS];
+    std::vector<uint8_t> h_ok[OG_MAX_CALLS];
+    std::vector<int64_t> h_tim[OG_MAX_CALLS];
+    bool host_ready = false;
+    uint32_t next_group = 0, next_row = 0;
+    /* record view backing store */
+    std::vector<std::vector<uint8_t>> rv_val, rv_bitmap;
+    std::vector<std::vector<int64_t>> rv_coltimes;
+    std::vector<int64_t> rv_times;
+    std::vector<og_colval_view> rv_cols;
+    int path_used = 0; /* 0 generic tile path, 1 fused */
+};

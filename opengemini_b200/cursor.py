@@ -1,0 +1,257 @@
+"""Python-side handles over the libogpu C ABI (used by tests, bench.py and smoke()).
+
+The call sequence mirrors how the reference drives this path (engine/iterators.go:130 CreateCursor ->
+aggregateCursor.SinkPlan -> KeyCursor.Next, engine/comm/cursor.go:46-56):
+
+    shard = Shard.open(...) | Shard.synth(...)       # TSSP pages + flattened ChunkMeta resident in HBM
+    q = AggQuery(shard, calls=[("sum", 0), ("count", 0)], interval=60e9, tmin=.., tmax=..)
+    q.run()                                          # kernels
+    for rec in q.records(): ...                      # Next(): ColVal-shaped views, (nil,nil,nil) == StopIteration
+    d = q.dense()                                    # device-resident dense interval record (torch views, zero copy)
+
+torch is used only as plumbing (device tensors over library-owned memory, NCCL in bench.py).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+_FUNCS = {"count": L.AGG_COUNT, "sum": L.AGG_SUM, "min": L.AGG_MIN, "max": L.AGG_MAX, "first": L.AGG_FIRST, "last": L.AGG_LAST}
+_OPS = {"<": L.OP_LT, "<=": L.OP_LTE, ">": L.OP_GT, ">=": L.OP_GTE, "=": L.OP_EQ, "==": L.OP_EQ, "!=": L.OP_NEQ}
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class _DevArray:
+    """__cuda_array_interface__ wrapper so torch.as_tensor() can view library-owned device memory."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, n, typestr, device):
+    import torch
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+
+
+class Shard:
+    def __init__(self, handle, keepalive=None):
+        self.h = C.c_void_p(handle)
+        self._keep = keepalive
+
+    @staticmethod
+    def init(device=0):
+        L.check(L.lib().og_init(device), "og_init")
+
+    @classmethod
+    def open(cls, data, sids, series_seg_begin, seg_tmin, seg_tmax, columns, time_page_off, time_page_len):
+        """columns: list of (name, type, page_off[u64], page_len[u32]); data: bytes/np.uint8 (host)."""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        sids = np.ascontiguousarray(sids, dtype=np.uint64)
+        ssb = np.ascontiguousarray(series_seg_begin, dtype=np.uint32)
+        tmin = np.ascontiguousarray(seg_tmin, dtype=np.int64)
+        tmax = np.ascontiguousarray(seg_tmax, dtype=np.int64)
+        tpo = np.ascontiguousarray(time_page_off, dtype=np.uint64)
+        tpl = np.ascontiguousarray(time_page_len, dtype=np.uint32)
+        cds = (L.ColumnDesc * max(1, len(columns)))()
+        keep = [data, sids, ssb, tmin, tmax, tpo, tpl]
+        for i, (name, typ, po, pl) in enumerate(columns):
+            po = np.ascontiguousarray(po, dtype=np.uint64)
+            pl = np.ascontiguousarray(pl, dtype=np.uint32)
+            keep += [po, pl]
+            cds[i].name = name.encode()
+            cds[i].type = typ
+            cds[i].page_off = _ptr(po, C.c_uint64)
+            cds[i].page_len = _ptr(pl, C.c_uint32)
+        d = L.ShardDesc()
+        d.data = _ptr(data, C.c_uint8)
+        d.data_len = data.size
+        d.n_series = sids.size
+        d.sids = _ptr(sids, C.c_uint64)
+        d.series_seg_begin = _ptr(ssb, C.c_uint32)
+        d.n_segments = tmin.size
+        d.seg_tmin = _ptr(tmin, C.c_int64)
+        d.seg_tmax = _ptr(tmax, C.c_int64)
+        d.n_columns = len(columns)
+        d.columns = cds
+        d.time_page_off = _ptr(tpo, C.c_uint64)
+        d.time_page_len = _ptr(tpl, C.c_uint32)
+        d.flags = 0
+        h = C.c_void_p()
+        L.check(L.lib().og_shard_open(C.byref(d), C.byref(h)), "og_shard_open")
+        return cls(h.value)
+
+    @classmethod
+    def open_desc(cls, desc, keepalive=None):
+        """Open from an already-built L.ShardDesc (e.g. one produced by the oracle's host builder in tests)."""
+        h = C.c_void_p()
+        L.check(L.lib().og_shard_open(C.byref(desc), C.byref(h)), "og_shard_open")
+        return cls(h.value, keepalive)
+
+    @classmethod
+    def synth(cls, n_series, rows_per_series, columns, t0=1_700_000_000_000_000_000, dt=1_000_000_000, seed=1,
+              rows_per_segment=1000):
+        """columns: list of (type, dist, null_permille). Builds the shard on the device with the encode kernels."""
+        cols = (L.SynthColumn * len(columns))()
+        for i, (t, dist, npm) in enumerate(columns):
+            cols[i].type, cols[i].dist, cols[i].null_permille = t, dist, npm
+        d = L.SynthDesc(n_series, rows_per_series, rows_per_segment, t0, dt, seed, len(columns), cols)
+        h = C.c_void_p()
+        L.check(L.lib().og_shard_synth(C.byref(d), C.byref(h)), "og_shard_synth")
+        return cls(h.value)
+
+    def info(self):
+        a = [C.c_uint64() for _ in range(4)]
+        t = [C.c_int64(), C.c_int64()]
+        L.check(L.lib().og_shard_info(self.h, *[C.byref(x) for x in a], C.byref(t[0]), C.byref(t[1])), "og_shard_info")
+        return dict(n_series=a[0].value, n_segments=a[1].value, n_rows=a[2].value, page_bytes=a[3].value, tmin=t[0].value, tmax=t[1].value)
+
+    def export(self):
+        lay = L.ShardLayout()
+        L.check(L.lib().og_shard_layout_get(self.h, C.byref(lay)), "og_shard_layout_get")
+        ns, ng, nc = lay.n_series, lay.n_segments, lay.n_columns
+        out = dict(data=np.empty(lay.data_len, np.uint8), sids=np.empty(ns, np.uint64), series_seg_begin=np.empty(ns + 1, np.uint32),
+                   seg_tmin=np.empty(ng, np.int64), seg_tmax=np.empty(ng, np.int64), page_off=np.empty((nc + 1, ng), np.uint64),
+                   page_len=np.empty((nc + 1, ng), np.uint32), col_types=np.empty(nc, np.int32))
+        L.check(L.lib().og_shard_export(self.h, *[out[k].ctypes.data for k in
+                                                   ("data", "sids", "series_seg_begin", "seg_tmin", "seg_tmax", "page_off", "page_len", "col_types")]),
+                "og_shard_export")
+        return out
+
+    def decode_segment(self, seg):
+        rv = L.RecordView()
+        L.check(L.lib().og_decode_segment(self.h, seg, C.byref(rv)), "og_decode_segment")
+        return _record_to_py(rv)
+
+    def close(self):
+        if self.h:
+            L.lib().og_shard_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _record_to_py(rv):
+    cols = []
+    for i in range(rv.n_cols):
+        cv = rv.cols[i]
+        raw = np.ctypeslib.as_array(cv.val, shape=(cv.val_bytes,)).copy() if cv.val_bytes else np.empty(0, np.uint8)
+        if cv.type == L.TYPE_FLOAT:
+            vals = raw.view(np.float64)
+        elif cv.type == L.TYPE_INT:
+            vals = raw.view(np.int64)
+        else:
+            vals = raw
+        nb = (cv.bitmap_offset + cv.len + 7) // 8
+        bm = np.ctypeslib.as_array(cv.bitmap, shape=(nb,)).copy() if nb else np.empty(0, np.uint8)
+        valid = np.unpackbits(bm, bitorder="little")[cv.bitmap_offset:cv.bitmap_offset + cv.len].astype(bool)
+        times = np.ctypeslib.as_array(cv.times, shape=(cv.len,)).copy() if cv.times else None
+        cols.append(dict(type=cv.type, values=vals, valid=valid, len=cv.len, nil_count=cv.nil_count, times=times))
+    times = np.ctypeslib.as_array(rv.times, shape=(rv.rows,)).copy() if rv.rows else np.empty(0, np.int64)
+    return dict(cols=cols, times=times, rows=rv.rows, group=rv.group, sid=rv.sid)
+
+
+class AggQuery:
+    """calls: list of (func_name, column); filter: RPN list of ("term", column, op, const) | "and" | "or"."""
+
+    def __init__(self, shard, calls, interval, tmin, tmax, offset=0, filter=None, group="all", series_group=None,
+                 n_groups=0, chunk_size=1024, flags=0):
+        self.shard = shard
+        self._calls = (L.Call * len(calls))()
+        for i, (f, c) in enumerate(calls):
+            self._calls[i].func = _FUNCS[f] if isinstance(f, str) else f
+            self._calls[i].column = c
+        flt = filter or []
+        self._filter = (L.FilterItem * max(1, len(flt)))()
+        for i, it in enumerate(flt):
+            if it in ("and", "or"):
+                self._filter[i].kind = L.F_AND if it == "and" else L.F_OR
+            else:
+                _, col, op, const = it
+                self._filter[i].kind = L.F_TERM
+                self._filter[i].column = col
+                self._filter[i].op = _OPS[op]
+                if isinstance(const, float):
+                    self._filter[i].const_is_float, self._filter[i].fval = 1, const
+                else:
+                    self._filter[i].const_is_float, self._filter[i].ival = 0, int(const)
+        d = L.QueryDesc()
+        d.interval, d.offset, d.tmin, d.tmax, d.ascending = int(interval), int(offset), int(tmin), int(tmax), 1
+        d.n_calls, d.calls = len(calls), self._calls
+        d.n_filter, d.filter = len(flt), self._filter
+        d.group_mode = {"all": L.GROUP_ALL, "series": L.GROUP_PER_SERIES, "map": L.GROUP_MAP}[group]
+        self._sg = None
+        if group == "map":
+            self._sg = np.ascontiguousarray(series_group, dtype=np.uint32)
+            d.series_group, d.n_groups = _ptr(self._sg, C.c_uint32), int(n_groups)
+        d.chunk_size, d.flags = chunk_size, flags
+        self.desc = d
+        self.h = C.c_void_p()
+        L.check(L.lib().og_query_create(shard.h, C.byref(d), C.byref(self.h)), "og_query_create")
+
+    def run(self):
+        L.check(L.lib().og_query_run(self.h), "og_query_run")
+        return self
+
+    def stats(self):
+        s = L.Stats()
+        L.check(L.lib().og_query_stats(self.h, C.byref(s)), "og_query_stats")
+        return {k: getattr(s, k) for k, _ in L.Stats._fields_}
+
+    def dense_view(self):
+        dv = L.DenseView()
+        L.check(L.lib().og_query_dense(self.h, C.byref(dv)), "og_query_dense")
+        return dv
+
+    def dense(self, device=None):
+        """Zero-copy torch views of the dense interval record: list of dict(values, valid, times|None, type, func)."""
+        import torch
+        dv = self.dense_view()
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        n = dv.n_groups * dv.n_buckets
+        cols = []
+        for i in range(dv.n_cols):
+            c = dv.cols[i]
+            vals = device_view(c.values, n, "<f8" if c.type == L.TYPE_FLOAT else "<i8", device)
+            valid = device_view(c.valid, n, "|u1", device)
+            times = device_view(c.times, n, "<i8", device) if c.times else None
+            cols.append(dict(values=vals, valid=valid, times=times, type=c.type, func=c.func))
+        return dict(n_groups=dv.n_groups, n_buckets=dv.n_buckets, start=dv.start, interval=dv.interval, cols=cols)
+
+    def dense_host(self):
+        d = self.dense()
+        for c in d["cols"]:
+            c["values"] = c["values"].cpu().numpy()
+            c["valid"] = c["valid"].cpu().numpy()
+            c["times"] = c["times"].cpu().numpy() if c["times"] is not None else None
+        return d
+
+    def records(self):
+        rv = L.RecordView()
+        while True:
+            st = L.lib().og_query_next(self.h, C.byref(rv))
+            if st == L.OG_EOF:
+                return
+            L.check(st, "og_query_next")
+            yield _record_to_py(rv)
+
+    def abort(self):
+        L.lib().og_query_abort(self.h)
+
+    def close(self):
+        if self.h:
+            L.lib().og_query_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,437 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar: bit-exact for everything, including float sums — the kernels keep the reference's summation order
+(left-to-right inside a record window, prev+curr across records, series order across series), so even float
+sums are compared bitwise here; tests that shard/chunk differently state their tolerance (1e-9 relative) explicitly.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from opengemini_b200 import AggQuery, Shard
+from opengemini_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+T0 = 1_700_000_000_000_000_000
+SEC = 1_000_000_000
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    Shard.init(0)
+
+
+def _bits(t):
+    a = t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
+    return a.view(np.uint64) if a.dtype != np.uint64 else a
+
+
+def compare_dense(gpu, ref, calls, multi, label=""):
+    assert gpu["n_groups"] == ref["n_groups"] and gpu["n_buckets"] == ref["n_buckets"], label
+    assert gpu["start"] == ref["start"], label
+    for k, (func, _col) in enumerate(calls):
+        g, r = gpu["cols"][k], ref["cols"][k]
+        gv = np.asarray(g["valid"]).astype(bool)
+        rv = r["valid"].astype(bool)
+        assert np.array_equal(gv, rv), f"{label} call {k} ({func}): validity differs at {np.flatnonzero(gv != rv)[:5]}"
+        gb, rb = _bits(g["values"])[rv], r["values"][rv]
+        bad = np.flatnonzero(gb != rb)
+        assert bad.size == 0, f"{label} call {k} ({func}): {bad.size} value cells differ, first at valid-index {bad[:3]}: gpu={gb[bad[:3]]} ref={rb[bad[:3]]}"
+        carries_time = func in ("min", "max", "first", "last") and not (multi and func in ("min", "max"))
+        if carries_time:
+            assert g["times"] is not None, f"{label} call {k}: missing times"
+            gt, rt = np.asarray(g["times"])[rv], r["times"][rv]
+            assert np.array_equal(gt, rt), f"{label} call {k} ({func}): row times differ"
+
+
+def run_both(shard, shard_desc, calls, interval, tmin, tmax, label, flags=0, **kw):
+    q = AggQuery(shard, calls, interval, tmin, tmax, flags=flags, **kw).run()
+    gpu = q.dense_host()
+    ref = oracle.scan(shard_desc, q.desc, threads=1)
+    compare_dense(gpu, ref, calls, len(calls) > 1, label)
+    st = q.stats()
+    assert st["rows_decoded"] == ref["rows_decoded"], label
+    assert st["page_bytes"] == ref["page_bytes"], label
+    q.close()
+    return gpu, ref
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K7: device encoders == restated reference encoders, byte for byte
+# ---------------------------------------------------------------------------------------------------------------
+SYNTH_COLS = [(L.TYPE_FLOAT, L.SYNTH_F_HI, 0), (L.TYPE_FLOAT, L.SYNTH_F_LO, 0), (L.TYPE_INT, L.SYNTH_INT_WALK, 0),
+              (L.TYPE_BOOL, L.SYNTH_BOOL, 0), (L.TYPE_FLOAT, L.SYNTH_F_HI, 50), (L.TYPE_INT, L.SYNTH_INT_WALK, 50),
+              (L.TYPE_BOOL, L.SYNTH_BOOL, 300), (L.TYPE_FLOAT, L.SYNTH_F_LO, 1000)]
+
+
+@pytest.mark.parametrize("rows", [2500, 1000, 1001, 7])
+def test_synth_pages_byte_exact(rows):
+    hs = oracle.HostShard(5, rows, SYNTH_COLS, t0=T0, dt=SEC, seed=42)
+    gs = Shard.synth(5, rows, SYNTH_COLS, t0=T0, dt=SEC, seed=42)
+    ex = gs.export()
+    nseg = ex["seg_tmin"].size
+    assert nseg == hs.desc.n_segments
+    assert np.array_equal(ex["seg_tmin"], np.ctypeslib.as_array(hs.desc.seg_tmin, shape=(nseg,)))
+    assert np.array_equal(ex["seg_tmax"], np.ctypeslib.as_array(hs.desc.seg_tmax, shape=(nseg,)))
+    for c in range(len(SYNTH_COLS) + 1):
+        for g in range(nseg):
+            off, ln = int(ex["page_off"][c, g]), int(ex["page_len"][c, g])
+            got = ex["data"][off:off + ln]
+            want = hs.page(c, g)
+            assert got.size == want.size and np.array_equal(got, want), \
+                f"column {c} segment {g}: device page ({got.size} B, head {got[:12]}) != oracle page ({want.size} B, head {want[:12]})"
+    gs.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K1-K4/K6: materialise path
+# ---------------------------------------------------------------------------------------------------------------
+def test_decode_segment_matches_oracle():
+    hs = oracle.HostShard(3, 2300, SYNTH_COLS, t0=T0, dt=SEC, seed=7)
+    sh = Shard.open_desc(hs.desc, keepalive=hs)
+    for seg in range(hs.desc.n_segments):
+        rec = sh.decode_segment(seg)
+        want_t = oracle.time_page_decode(hs.page(len(SYNTH_COLS), seg))
+        assert np.array_equal(rec["times"], want_t)
+        for c, (typ, _d, _n) in enumerate(SYNTH_COLS):
+            wv, wvalid = oracle.field_page_decode(typ, hs.page(c, seg))
+            col = rec["cols"][c]
+            assert col["len"] == wvalid.size and col["nil_count"] == int((~wvalid).sum())
+            assert np.array_equal(col["valid"], wvalid), f"seg {seg} col {c} bitmap"
+            assert np.array_equal(col["values"].view(np.uint8), wv.view(np.uint8)), f"seg {seg} col {c} values"
+    sh.close()
+
+
+def _one_segment_shard(typ, page, time_page, rows_t):
+    data = np.concatenate([page, time_page])
+    return Shard.open(data, [1], [0, 1], [rows_t[0]], [rows_t[-1]], [("v", typ, [0], [page.size])], [page.size], [time_page.size])
+
+
+@pytest.mark.parametrize("shape", ["raw", "same", "same0", "rle", "rle0", "gorilla", "gorilla_wrap", "one", "empty", "nulls"])
+def test_float_codecs_decode(shape):
+    rng = np.random.default_rng(3)
+    n = 1000
+    valid = None
+    if shape == "raw":
+        v = rng.integers(0, 2**63, n).view(np.float64)
+        v = np.where(np.isfinite(v), v, 1.0)
+    elif shape == "same":
+        v = np.full(n, 3.25)
+    elif shape == "same0":
+        v = np.zeros(n)
+    elif shape == "rle":
+        v = np.repeat([1.5, 2.5, 0.0, 7.0], n // 4)
+    elif shape == "rle0":
+        v = np.repeat([0.0, 4.0, 0.0, 0.0, 9.0], n // 5)
+    elif shape == "gorilla":
+        v = 100 + rng.random(n)
+    elif shape == "gorilla_wrap":
+        v = (np.uint64(0x4059000000000000) + rng.integers(0, 1000, n).astype(np.uint64)).view(np.float64)
+    elif shape == "one":
+        v = np.array([42.5]); n = 1
+    elif shape == "empty":
+        v = np.zeros(n); valid = np.zeros(n, np.uint8)
+    else:
+        v = 100 + rng.random(n); valid = (rng.random(n) > 0.1).astype(np.uint8)
+    page = oracle.field_page_encode(L.TYPE_FLOAT, v, valid)
+    t = T0 + np.arange(n, dtype=np.int64) * SEC
+    sh = _one_segment_shard(L.TYPE_FLOAT, page, oracle.time_page_encode(t), t)
+    rec = sh.decode_segment(0)
+    wv, wvalid = oracle.field_page_decode(L.TYPE_FLOAT, page)
+    assert np.array_equal(rec["cols"][0]["valid"], wvalid)
+    assert np.array_equal(rec["cols"][0]["values"].view(np.uint64), wv.view(np.uint64))
+    sh.close()
+
+
+@pytest.mark.parametrize("shape", ["const", "s8b", "s8b_ones", "raw2", "bigdelta", "nulls"])
+def test_int_codecs_decode(shape):
+    rng = np.random.default_rng(5)
+    n = 1000
+    valid = None
+    if shape == "const":
+        v = np.arange(n, dtype=np.int64) * -7 + 3
+    elif shape == "s8b":
+        v = np.cumsum(rng.integers(-1000, 1001, n)).astype(np.int64)
+    elif shape == "s8b_ones":
+        v = -np.arange(n, dtype=np.int64); v[-1] += 5
+    elif shape == "raw2":
+        v = np.array([5, -9], np.int64); n = 2
+    elif shape == "bigdelta":
+        v = np.where(np.arange(n) % 2 == 0, 1 << 40, -(1 << 40)).astype(np.int64)
+    else:
+        v = np.cumsum(rng.integers(-50, 51, n)).astype(np.int64); valid = (rng.random(n) > 0.2).astype(np.uint8)
+    page = oracle.field_page_encode(L.TYPE_INT, v, valid)
+    t = T0 + np.arange(n, dtype=np.int64) * SEC
+    sh = _one_segment_shard(L.TYPE_INT, page, oracle.time_page_encode(t), t)
+    rec = sh.decode_segment(0)
+    wv, wvalid = oracle.field_page_decode(L.TYPE_INT, page)
+    assert np.array_equal(rec["cols"][0]["valid"], wvalid)
+    assert np.array_equal(rec["cols"][0]["values"], wv)
+    sh.close()
+
+
+@pytest.mark.parametrize("shape", ["const", "s8b_scaled", "s8b_unscaled", "raw2", "one"])
+def test_time_codecs_decode(shape):
+    rng = np.random.default_rng(9)
+    if shape == "const":
+        t = T0 + np.arange(1000, dtype=np.int64) * SEC
+    elif shape == "s8b_scaled":
+        t = T0 + np.cumsum(rng.integers(1, 50, 1000) * 1_000_000).astype(np.int64)
+    elif shape == "s8b_unscaled":
+        t = T0 + np.cumsum(rng.integers(1, 5000, 777)).astype(np.int64)
+    elif shape == "raw2":
+        t = np.array([T0, T0 + 17], np.int64)
+    else:
+        t = np.array([T0 + 5], np.int64)
+    v = np.arange(t.size, dtype=np.float64) * 1.5 + 0.25
+    page = oracle.field_page_encode(L.TYPE_FLOAT, v)
+    sh = _one_segment_shard(L.TYPE_FLOAT, page, oracle.time_page_encode(t), t)
+    rec = sh.decode_segment(0)
+    assert np.array_equal(rec["times"], t)
+    # and through the fused + generic aggregate paths: irregular time pages drive the TimeIter
+    for flags in (0, L.Q_NO_FUSED):
+        q = AggQuery(sh, [("sum", 0), ("count", 0), ("max", 0)], 7 * SEC, int(t[0]), int(t[-1]), flags=flags).run()
+        d = q.dense_host()
+        b = (t - d["start"]) // (7 * SEC)
+        want_cnt = np.bincount(b, minlength=d["n_buckets"])
+        assert np.array_equal(d["cols"][1]["values"] * d["cols"][1]["valid"], want_cnt)
+        q.close()
+    sh.close()
+
+
+def test_unsupported_and_corrupt_pages_fail_cleanly():
+    n = 100
+    t = T0 + np.arange(n, dtype=np.int64) * SEC
+    tp = oracle.time_page_encode(t)
+    good = oracle.field_page_encode(L.TYPE_FLOAT, 100 + np.random.default_rng(1).random(n))
+    for tag, want in ((0x20, L.OG_E_UNSUPPORTED), (0x60, L.OG_E_UNSUPPORTED), (0x70, L.OG_E_CORRUPT)):
+        bad = good.copy(); bad[5] = tag  # block tag byte after the 5-byte Full header
+        with pytest.raises(L.OgpuError) as ei:
+            _one_segment_shard(L.TYPE_FLOAT, bad, tp, t)
+        assert ei.value.status == want
+    ipage = oracle.field_page_encode(L.TYPE_INT, np.arange(n, dtype=np.int64) ** 2)
+    bad = ipage.copy(); bad[5] = 0x30  # zstd
+    with pytest.raises(L.OgpuError) as ei:
+        _one_segment_shard(L.TYPE_INT, bad, tp, t)
+    assert ei.value.status == L.OG_E_UNSUPPORTED
+    # type mismatch on a page with a normal (partial-null) header
+    valid = np.ones(n, np.uint8); valid[3] = 0
+    fpage = oracle.field_page_encode(L.TYPE_FLOAT, np.ones(n), valid)
+    with pytest.raises(L.OgpuError) as ei:
+        _one_segment_shard(L.TYPE_INT, fpage, tp, t)
+    assert ei.value.status == L.OG_E_TYPE
+    # descending scans are rejected, not mis-executed
+    sh = _one_segment_shard(L.TYPE_FLOAT, good, tp, t)
+    d = L.QueryDesc(); calls = (L.Call * 1)(); calls[0].func, calls[0].column = L.AGG_SUM, 0
+    d.interval, d.tmin, d.tmax, d.ascending, d.n_calls, d.calls = SEC, int(t[0]), int(t[-1]), 0, 1, calls
+    h = C.c_void_p()
+    assert L.lib().og_query_create(sh.h, C.byref(d), C.byref(h)) == L.OG_E_UNSUPPORTED
+    sh.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K5: aggregate parity (fused and generic paths) against the reference-structured oracle
+# ---------------------------------------------------------------------------------------------------------------
+AGG_COLS = [(L.TYPE_FLOAT, L.SYNTH_F_HI, 0), (L.TYPE_INT, L.SYNTH_INT_WALK, 0), (L.TYPE_BOOL, L.SYNTH_BOOL, 0),
+            (L.TYPE_FLOAT, L.SYNTH_F_LO, 50), (L.TYPE_INT, L.SYNTH_INT_WALK, 200), (L.TYPE_BOOL, L.SYNTH_BOOL, 100)]
+
+
+@pytest.fixture(scope="module")
+def agg_shard():
+    hs = oracle.HostShard(7, 4321, AGG_COLS, t0=T0, dt=SEC, seed=11)
+    sh = Shard.open_desc(hs.desc, keepalive=hs)
+    yield sh, hs
+    sh.close()
+
+
+ALL6 = ["count", "sum", "min", "max", "first", "last"]
+
+
+@pytest.mark.parametrize("flags", [0, L.Q_NO_FUSED], ids=["fused", "generic"])
+@pytest.mark.parametrize("interval", [60 * SEC, 7 * SEC, 3600 * SEC, 0])
+@pytest.mark.parametrize("col", [0, 1, 3, 4])
+def test_single_call_aggregates(agg_shard, col, interval, flags):
+    sh, hs = agg_shard
+    tmin, tmax = T0, T0 + 4320 * SEC
+    for f in ALL6:
+        run_both(sh, hs.desc, [(f, col)], interval, tmin, tmax, f"{f}(col{col}) iv={interval} flags={flags}", flags=flags)
+
+
+@pytest.mark.parametrize("flags", [0, L.Q_NO_FUSED], ids=["fused", "generic"])
+@pytest.mark.parametrize("col", [0, 1, 3, 4])
+def test_multi_call_aggregates(agg_shard, col, flags):
+    sh, hs = agg_shard
+    for interval in (60 * SEC, 1000 * SEC, 0):
+        run_both(sh, hs.desc, [(f, col) for f in ALL6], interval, T0, T0 + 4320 * SEC, f"all6(col{col}) iv={interval}", flags=flags)
+    run_both(sh, hs.desc, [("sum", col), ("count", col)], 60 * SEC, T0, T0 + 4320 * SEC, "mean", flags=flags)
+
+
+@pytest.mark.parametrize("col", [2, 5])
+def test_bool_aggregates(agg_shard, col):
+    sh, hs = agg_shard
+    for flags in (0, L.Q_NO_FUSED):
+        for f in ("count", "min", "max", "first", "last"):
+            run_both(sh, hs.desc, [(f, col)], 60 * SEC, T0, T0 + 4320 * SEC, f"{f}(bool{col})", flags=flags)
+        run_both(sh, hs.desc, [(f, col) for f in ("count", "min", "max", "first", "last")], 90 * SEC, T0, T0 + 4320 * SEC, "bool multi", flags=flags)
+
+
+@pytest.mark.parametrize("flags", [0, L.Q_NO_FUSED], ids=["fused", "generic"])
+def test_time_range_and_offset(agg_shard, flags):
+    sh, hs = agg_shard
+    # range cutting segments in the middle, windows not aligned to the range, GROUP BY time(1m, 7s)
+    run_both(sh, hs.desc, [("sum", 0), ("count", 0)], 60 * SEC, T0 + 1234 * SEC + 5, T0 + 3456 * SEC + 7, "mid-range", flags=flags)
+    run_both(sh, hs.desc, [("max", 0)], 60 * SEC, T0 + 999 * SEC, T0 + 1001 * SEC, "two-row range", flags=flags)
+    run_both(sh, hs.desc, [("first", 3)], 60 * SEC, T0 - 500 * SEC, T0 + 10_000 * SEC, "range wider than data", flags=flags)
+    run_both(sh, hs.desc, [("sum", 1), ("last", 1)], 60 * SEC, T0, T0 + 4320 * SEC, "offset 7s", flags=flags, offset=7 * SEC)
+    run_both(sh, hs.desc, [("min", 4)], 61 * SEC, T0 + 17, T0 + 4000 * SEC, "odd interval", flags=flags, offset=-13 * SEC)
+
+
+@pytest.mark.parametrize("group", ["series", "map"])
+def test_group_modes(agg_shard, group):
+    sh, hs = agg_shard
+    kw = dict(group=group)
+    if group == "map":
+        kw.update(series_group=[2, 0, 1, 0, 2, 2, 0], n_groups=3)
+    for flags in (0, L.Q_NO_FUSED):
+        for calls in ([("sum", 0), ("count", 0)], [("max", 0)], [("first", 4)], [(f, 3) for f in ALL6]):
+            run_both(sh, hs.desc, calls, 60 * SEC, T0, T0 + 4320 * SEC, f"group={group} {calls}", flags=flags, **kw)
+
+
+def test_where_filters(agg_shard):
+    sh, hs = agg_shard
+    cases = [
+        [("term", 0, ">", 100.5)],
+        [("term", 0, "<", 100.25)],
+        [("term", 1, ">=", 0)],
+        [("term", 1, "<", 100.5)],                       # int column against a float constant (Int64ToFloat64Slice)
+        [("term", 2, "=", 1)],
+        [("term", 3, ">", 1000.0), ("term", 5, "!=", 1), "and"],
+        [("term", 0, ">", 100.9), ("term", 4, "<", -2000), "or"],
+        [("term", 0, ">", 100.2), ("term", 0, "<=", 100.8), "and", ("term", 2, "=", 0), "or"],
+        [("term", 0, ">", 200.0)],                       # nothing survives
+    ]
+    for flt in cases:
+        run_both(sh, hs.desc, [("count", 1), ("sum", 1), ("sum", 0), ("count", 2)], 60 * SEC, T0, T0 + 4320 * SEC, f"where {flt}", filter=flt)
+        run_both(sh, hs.desc, [("max", 3)], 300 * SEC, T0 + 100 * SEC, T0 + 4000 * SEC, f"where {flt} max", filter=flt)
+        run_both(sh, hs.desc, [("first", 4)], 3600 * SEC, T0, T0 + 4320 * SEC, f"where {flt} first", filter=flt, group="series")
+
+
+def test_nan_and_tie_semantics():
+    """NaN handling (strict compares, sticky first NaN) and tie-breaks must follow the reducers exactly."""
+    n = 1000
+    rng = np.random.default_rng(21)
+    series = []
+    for s in range(4):
+        v = np.round(rng.random(3 * n) * 4) / 4  # many ties
+        v[rng.integers(0, 3 * n, 40)] = np.nan
+        if s == 1:
+            v[0] = np.nan  # window that starts with NaN
+            v[n] = np.nan  # record (segment) that starts with NaN inside a window spanning two segments
+        series.append(v)
+    pages, tpages, tmins, tmaxs = [], [], [], []
+    for s in range(4):
+        for g in range(3):
+            seg = series[s][g * n:(g + 1) * n]
+            pages.append(oracle.field_page_encode(L.TYPE_FLOAT, seg))
+            t = T0 + (np.arange(n, dtype=np.int64) + g * n) * SEC
+            tpages.append(oracle.time_page_encode(t)); tmins.append(t[0]); tmaxs.append(t[-1])
+    blob, offs, lens = [], [], []
+    pos = 0
+    for p in pages + tpages:
+        offs.append(pos); lens.append(p.size); blob.append(p); pos += p.size
+    data = np.concatenate(blob)
+    nseg = 12
+    sh = Shard.open(data, [1, 2, 3, 4], [0, 3, 6, 9, 12], tmins, tmaxs, [("v", L.TYPE_FLOAT, offs[:nseg], lens[:nseg])], offs[nseg:], lens[nseg:])
+    ex = sh.export()
+    sd = oracle.shard_desc_from_export(ex)
+    for flags in (0, L.Q_NO_FUSED):
+        for iv in (60 * SEC, 700 * SEC):
+            for f in ALL6:
+                run_both(sh, sd, [(f, 0)], iv, T0, T0 + 3 * n * SEC, f"nan {f} iv={iv}", flags=flags)
+            run_both(sh, sd, [(f, 0) for f in ALL6], iv, T0, T0 + 3 * n * SEC, "nan multi", flags=flags)
+            run_both(sh, sd, [("max", 0)], iv, T0, T0 + 3 * n * SEC, "nan max per series", flags=flags, group="series")
+    sh.close()
+
+
+def test_records_next_matches_dense(agg_shard):
+    sh, hs = agg_shard
+    q = AggQuery(sh, [("sum", 3), ("count", 3), ("last", 3)], 60 * SEC, T0, T0 + 4320 * SEC, group="series", chunk_size=16).run()
+    d = q.dense_host()
+    nb = d["n_buckets"]
+    seen = 0
+    for rec in q.records():
+        g = rec["group"]
+        assert rec["sid"] == g + 1
+        assert rec["rows"] <= 16
+        b = (rec["times"] - d["start"]) // (60 * SEC)
+        for k in range(3):
+            col = rec["cols"][k]
+            cells = g * nb + b
+            assert np.array_equal(col["valid"], d["cols"][k]["valid"][cells].astype(bool))
+            want = d["cols"][k]["values"][cells][col["valid"]]
+            assert np.array_equal(col["values"].view(np.uint64), want.view(np.uint64))
+        assert rec["cols"][2]["times"] is not None  # RecMeta.Times for last() in a multi-call query
+        seen += rec["rows"]
+    any_valid = np.zeros(d["n_groups"] * nb, bool)
+    for k in range(3):
+        any_valid |= d["cols"][k]["valid"].astype(bool)
+    assert seen == int(any_valid.sum())
+    q.close()
+
+
+def test_larger_shard_properties():
+    """Size-independent checks on a shard the oracle would take long on: counts add up, sums are linear,
+    fused == generic bitwise, per-series folds to all-series."""
+    n_series, rows = 300, 20_000
+    sh = Shard.synth(n_series, rows, [(L.TYPE_FLOAT, L.SYNTH_F_HI, 0)], t0=T0, dt=SEC, seed=5)
+    info = sh.info()
+    assert info["n_rows"] == n_series * rows and info["n_segments"] == n_series * 20
+    tmax = T0 + (rows - 1) * SEC
+    qa = AggQuery(sh, [("sum", 0), ("count", 0), ("max", 0), ("min", 0)], 60 * SEC, T0, tmax).run()
+    qb = AggQuery(sh, [("sum", 0), ("count", 0), ("max", 0), ("min", 0)], 60 * SEC, T0, tmax, flags=L.Q_NO_FUSED).run()
+    a, b = qa.dense_host(), qb.dense_host()
+    for k in range(4):
+        assert np.array_equal(a["cols"][k]["valid"], b["cols"][k]["valid"])
+        assert np.array_equal(_bits(a["cols"][k]["values"]), _bits(b["cols"][k]["values"]))
+    cnt = a["cols"][1]["values"]
+    assert int(cnt.sum()) == n_series * rows
+    assert np.all(a["cols"][2]["values"][a["cols"][2]["valid"] > 0] < 101.0) and np.all(a["cols"][3]["values"][a["cols"][3]["valid"] > 0] >= 100.0)
+    mean = a["cols"][0]["values"] / np.maximum(cnt, 1)
+    assert np.all(np.abs(mean[cnt > 0] - 100.5) < 0.05)
+    qs = AggQuery(sh, [("sum", 0), ("count", 0)], 60 * SEC, T0, tmax, group="series").run()
+    s = qs.dense_host()
+    per = s["cols"][0]["values"].reshape(n_series, -1)
+    # folding the per-series sums in series order reproduces the all-series sums bitwise
+    acc = np.zeros(per.shape[1])
+    for i in range(n_series):
+        acc = per[i] + acc
+    assert np.array_equal(acc.view(np.uint64), a["cols"][0]["values"].view(np.uint64))
+    assert np.array_equal(s["cols"][1]["values"].reshape(n_series, -1).sum(0), cnt)
+    for q in (qa, qb, qs):
+        q.close()
+    sh.close()
+
+
+def test_encode_pages_roundtrip_on_device():
+    """og_encode_pages (K7) output decodes back to the input through og_shard_open + og_decode_segment."""
+    import torch
+    rng = np.random.default_rng(8)
+    nseg, rps = 6, 1000
+    vals = np.cumsum(rng.integers(-3, 4, nseg * rps)).astype(np.float64)
+    dv = torch.from_numpy(vals).cuda()
+    out = torch.zeros(nseg * 8704, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(nseg, dtype=torch.int64, device="cuda")
+    ln = torch.zeros(nseg, dtype=torch.int32, device="cuda")
+    total = C.c_uint64()
+    L.check(L.lib().og_encode_pages(L.TYPE_FLOAT, 0, dv.data_ptr(), None, None, nseg, rps, out.data_ptr(), out.numel(),
+                                    off.data_ptr(), ln.data_ptr(), C.byref(total)), "og_encode_pages")
+    pages = out.cpu().numpy()
+    offs, lens = off.cpu().numpy(), ln.cpu().numpy()
+    assert int(lens.sum()) == total.value
+    for g in range(nseg):
+        want = oracle.field_page_encode(L.TYPE_FLOAT, vals[g * rps:(g + 1) * rps])
+        got = pages[offs[g]:offs[g] + lens[g]]
+        assert np.array_equal(got, want), f"segment {g}"
