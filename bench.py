@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — decoded+aggregated rows/s of the fused scan/aggregate path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (libogpu.so, sm_100a kernels)
+    python bench.py --impl reference --gpus N ...          # reference arm: the CPU oracle on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] — one TSM shard of 10k series x 1M points/series of float64
+(G-hi distribution: 100 + U[0,1) with full mantissa tail -> Gorilla ~6 B/value), 1 s cadence, const-delta time pages,
+1000-row segments; SELECT sum, count (mean) and max GROUP BY time(1m), all series in one tagset.
+A "step" = one og_query_run over the whole HBM-resident shard (one k_fused_segment launch + edge stitch + tagset
+merge).  At N > 1 every rank holds its own shard (distinct seed; configs[3]) and a step ends with the NCCL
+cross-shard merge of the dense bucket arrays (weak scaling).
+
+The JSON line follows the driver contract; `roofline` is the fused kernel alone, `e2e` goes through the C ABI with
+host buffers (og_shard_open H2D + query + og_query_next D2H inside the timed region), `cpu_baseline` is the oracle.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+T0, SEC = 1_700_000_000_000_000_000, 1_000_000_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--series", type=int, default=10_000)
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dist", default="hi", choices=["hi", "lo"])
+    ap.add_argument("--e2e-series", type=int, default=2000, help="series of the host-resident sample used by the e2e leg")
+    ap.add_argument("--cpu-series", type=int, default=0, help="series of the CPU sample (0 = auto: 4 per host thread)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_name(a):
+    return (f"configs[1]: {a.series} series x {a.rows} float64 points/series, G-{a.dist} (Gorilla), 1s cadence, 1000-row segments, "
+            f"sum+count(mean)+max GROUP BY time(1m), one tagset")
+
+
+def dist_const(L, a):
+    return L.SYNTH_F_HI if a.dist == "hi" else L.SYNTH_F_LO
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm on the host cores (the Go engine cannot be built in this image: the
+# oracle is its C++ restatement, see oracle/og_oracle.h)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_sample(L, a, n_series, threads):
+    import oracle
+    hs = oracle.HostShard(n_series, a.rows, [(L.TYPE_FLOAT, dist_const(L, a), 0)], t0=T0, dt=SEC, seed=1000, threads=threads)
+    return hs
+
+
+def query_desc(L, a):
+    calls = (L.Call * 3)()
+    for i, f in enumerate((L.AGG_SUM, L.AGG_COUNT, L.AGG_MAX)):
+        calls[i].func, calls[i].column = f, 0
+    d = L.QueryDesc()
+    d.interval, d.offset, d.tmin, d.tmax, d.ascending = 60 * SEC, 0, T0, T0 + (a.rows - 1) * SEC, 1
+    d.n_calls, d.calls, d.n_filter, d.group_mode, d.chunk_size = 3, calls, 0, L.GROUP_ALL, 1024
+    d._keep = calls
+    return d
+
+
+def run_reference(a):
+    from opengemini_b200 import _lib as L
+    import oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = a.cpu_series or min(a.series, 4 * threads)
+    hs = cpu_sample(L, a, n, threads)
+    qd = query_desc(L, a)
+    rows = n * a.rows
+    for _ in range(a.warmup):
+        oracle.scan(hs.desc, qd, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        r = oracle.scan(hs.desc, qd, threads=threads)
+    dt = time.perf_counter() - t0
+    v = rows * a.steps / dt
+    line = {"impl": "reference", "metric": "decoded+aggregated rows/s", "value": v, "unit": "rows/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(a), "sample": f"{n} series x {a.rows} rows per step"},
+            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} series x {a.rows} rows ({rows} rows, {r['page_bytes']} page bytes) per step, C++ restatement of the reference pull loop"},
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def cross_shard_merge(torch, dist, q, dense, world):
+    """configs[3]: NCCL merge of the dense bucket arrays.  sum/count: all-reduce; selectors: all-gather + ordered fold
+    (og_query_merge_dense keeps the reference's tie-breaks, lib/record/reccord_functions.go:482-494)."""
+    from opengemini_b200 import _lib as L
+    sel_cols = []
+    for i, c in enumerate(dense["cols"]):
+        if c["func"] in (L.AGG_SUM, L.AGG_COUNT):
+            dist.all_reduce(c["values"], op=dist.ReduceOp.SUM)
+            dist.all_reduce(c["valid"], op=dist.ReduceOp.MAX)
+        else:
+            sel_cols.append(i)
+    if not sel_cols:
+        return
+    gathered = {}
+    for i in sel_cols:
+        c = dense["cols"][i]
+        gv = [torch.empty_like(c["values"]) for _ in range(world)]
+        gk = [torch.empty_like(c["valid"]) for _ in range(world)]
+        dist.all_gather(gv, c["values"])
+        dist.all_gather(gk, c["valid"])
+        gt = None
+        if c["times"] is not None:
+            gt = [torch.empty_like(c["times"]) for _ in range(world)]
+            dist.all_gather(gt, c["times"])
+        gathered[i] = (gv, gk, gt)
+    # fold ranks 0..world-1 in rank order on every rank: start from rank 0's partial
+    for i in sel_cols:
+        c = dense["cols"][i]
+        gv, gk, gt = gathered[i]
+        c["values"].copy_(gv[0]); c["valid"].copy_(gk[0])
+        if gt is not None:
+            c["times"].copy_(gt[0])
+    torch.cuda.synchronize()
+    dv = q.dense_view()
+    for r in range(1, world):
+        cols = (L.DenseCol * dv.n_cols)()
+        for i in range(dv.n_cols):
+            cols[i] = dv.cols[i]
+            if i in gathered:
+                gv, gk, gt = gathered[i]
+                cols[i].values, cols[i].valid = gv[r].data_ptr(), gk[r].data_ptr()
+                cols[i].times = gt[r].data_ptr() if gt is not None else None
+        other = L.DenseView(dv.n_groups, dv.n_buckets, dv.start, dv.interval, dv.n_cols, cols, None)
+        # sum/count columns were already all-reduced: give the fold an all-invalid partial for them
+        zero_ok = torch.zeros(dv.n_groups * dv.n_buckets, dtype=torch.uint8, device=dense["cols"][0]["valid"].device)
+        for i in range(dv.n_cols):
+            if i not in gathered:
+                cols[i].valid = zero_ok.data_ptr()
+        L.check(L.lib().og_query_merge_dense(q.h, C.byref(other)), "og_query_merge_dense")
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    from opengemini_b200 import AggQuery, Shard
+    from opengemini_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    Shard.init(local)
+    dev = torch.device("cuda", local)
+    cols = [(L.TYPE_FLOAT, dist_const(L, a), 0)]
+    t_gen = time.perf_counter()
+    sh = Shard.synth(a.series, a.rows, cols, t0=T0, dt=SEC, seed=1000 + rank)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t_gen
+    info = sh.info()
+    calls = [("sum", 0), ("count", 0), ("max", 0)]
+    tmax = T0 + (a.rows - 1) * SEC
+    q = AggQuery(sh, calls, 60 * SEC, T0, tmax)
+
+    def step():
+        q.run()
+        st = q.stats()
+        ms = st["kernel_ms"]
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cross_shard_merge(torch, dist, q, q.dense(dev), world)
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms, st
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    dev_ms, main_ms, launches = 0.0, 0.0, 0
+    for _ in range(a.steps):
+        ms, st = step()
+        dev_ms += ms
+        main_ms += st["main_kernel_ms"]
+        launches += st["kernel_launches"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_s = time.perf_counter() - w0
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms, wall_s * 1e3], dtype=torch.float64, device=dev)
+    rows_t = torch.tensor([float(st["rows_decoded"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rows_t, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max = t.tolist()
+    total_rows = rows_t.item()
+    value = total_rows * a.steps / (dev_ms_max / 1e3)
+
+    # roofline of the dominant kernel (k_fused_segment): algorithmic bytes per launch / its average duration
+    peak, peak_src = measured_peak()
+    algo_bytes = st["page_bytes"] + st["dir_bytes"] + 16667 * 3 * 8  # pages + 32 B/segment directory + dense output
+    main_per_launch_ms = main_ms / a.steps
+    achieved = algo_bytes / (main_per_launch_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_fused_segment<3>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                "bytes_per_row": algo_bytes / max(1, st["rows_decoded"]), "kernel_ms": main_per_launch_ms,
+                "share_of_step": main_ms / max(1e-9, dev_ms if world == 1 else main_ms)}
+
+    # e2e: the call a user of the C ABI makes, with HOST buffers (pinned), H2D + query + D2H in the timed region
+    e2e = None
+    e2e_launches = 0
+    if not a.no_e2e:
+        ns = min(a.e2e_series, a.series)
+        small = Shard.synth(ns, a.rows, cols, t0=T0, dt=SEC, seed=1000 + rank)
+        lay = L.ShardLayout()
+        L.check(L.lib().og_shard_layout_get(small.h, C.byref(lay)), "layout")
+        pinned = torch.empty(lay.data_len, dtype=torch.uint8, pin_memory=True)
+        ex = dict(sids=np.empty(ns, np.uint64), series_seg_begin=np.empty(ns + 1, np.uint32), seg_tmin=np.empty(lay.n_segments, np.int64),
+                  seg_tmax=np.empty(lay.n_segments, np.int64), page_off=np.empty((2, lay.n_segments), np.uint64),
+                  page_len=np.empty((2, lay.n_segments), np.uint32), col_types=np.empty(1, np.int32))
+        L.check(L.lib().og_shard_export(small.h, pinned.data_ptr(), *[ex[k].ctypes.data for k in
+                                                                        ("sids", "series_seg_begin", "seg_tmin", "seg_tmax", "page_off", "page_len", "col_types")]), "export")
+        small.close()
+        host_data = pinned.numpy()
+        h2d = int(lay.data_len + lay.n_segments * (2 * 12 + 16) + ns * 12)
+        e_steps = max(1, min(a.steps, 3))
+
+        def e2e_step():
+            s2 = Shard.open(host_data, ex["sids"], ex["series_seg_begin"], ex["seg_tmin"], ex["seg_tmax"],
+                            [("f0", L.TYPE_FLOAT, ex["page_off"][0], ex["page_len"][0])], ex["page_off"][1], ex["page_len"][1])
+            q2 = AggQuery(s2, calls, 60 * SEC, T0, tmax).run()
+            out_rows, d2h = 0, 0
+            for rec in q2.records():
+                out_rows += rec["rows"]
+                d2h += sum(c["values"].nbytes + (c["len"] + 7) // 8 for c in rec["cols"]) + rec["times"].nbytes
+            ln = q2.stats()["kernel_launches"] + 2
+            q2.close(); s2.close()
+            return out_rows, d2h, ln
+
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            out_rows, d2h, ln = e2e_step()
+            e2e_launches += ln
+        torch.cuda.synchronize()
+        et = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        e_rows = ns * a.rows * world
+        # d2h: the three dense columns (value + validity) are copied back whole before records are sliced
+        d2h_full = 16667 * 3 * 9
+        e2e = {"value": e_rows * e_steps / et.item(), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": max(d2h, d2h_full),
+               "sample": f"{ns} series x {a.rows} rows per GPU per step (host-resident, pinned), og_shard_open + og_query_run + og_query_next",
+               "steps": e_steps, "ms_per_step": et.item() / e_steps * 1e3, "out_rows": out_rows}
+        del pinned
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        import oracle
+        threads = os.cpu_count() or 1
+        n = a.cpu_series or min(a.series, 4 * threads)
+        hs = cpu_sample(L, a, n, threads)
+        qd = query_desc(L, a)
+        oracle.scan(hs.desc, qd, threads=threads, s1=min(n, threads))  # warm
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            r = oracle.scan(hs.desc, qd, threads=threads)
+            reps += 1
+            el = time.perf_counter() - t0
+            if el > 8 or reps >= 20:
+                break
+        t1 = time.perf_counter()
+        r1 = oracle.scan(hs.desc, qd, threads=1, s1=1)
+        one = a.rows / (time.perf_counter() - t1)
+        cpu = {"value": n * a.rows * reps / el, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"{n} series x {a.rows} rows x {reps} repetitions in {el:.1f}s; C++ restatement of the reference pull loop "
+                         f"(decode -> FilterByTime -> aggregateCursor -> AggTagSet merge), series strided over {threads} threads",
+               "single_thread_rows_per_s": one, "decoded_MBps_per_thread": one * 8 / 1e6}
+        del r1
+
+    if rank == 0:
+        line = {"metric": "decoded+aggregated rows/s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "impl": "ours",
+                "config": {"workload": workload_name(a), "shards": world, "rows_per_shard": int(info["n_rows"]), "segments_per_shard": int(info["n_segments"]),
+                           "page_bytes_per_shard": int(info["page_bytes"]), "compressed_bytes_per_value": info["page_bytes"] / max(1, info["n_rows"]),
+                           "l2": "inputs (tens of GB per step) are far larger than the 126 MB L2; no explicit flush",
+                           "parallelism": f"shard-per-gpu x{world}" + (", NCCL all-reduce(sum,count) + all-gather/fold(max)" if world > 1 else ""),
+                           "timing": "CUDA events on the query stream (og_stats.kernel_ms) + torch events around the NCCL merge; max over ranks",
+                           "synth_seconds": gen_s},
+                "wall_ms_per_step": wall_ms_max / a.steps, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "gpu_launches": launches + e2e_launches}
+        print(json.dumps(line), flush=True)
+    q.close()
+    sh.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -186,7 +186,9 @@ typedef struct og_stats {
     uint64_t out_bytes;        /* dense output bytes */
     double kernel_ms;          /* device time of the last og_query_run (CUDA events on the query stream) */
     double h2d_ms;
+    double main_kernel_ms;     /* of which: the dominant decode+reduce kernel(s) (k_fused_segment, or decode/filter/reduce tiles) */
     uint32_t kernel_launches;  /* kernels launched by the last og_query_run */
+    int32_t path;              /* 1 = fused kernel, 0 = generic materialise-tile path */
 } og_stats;
 
 typedef struct og_shard og_shard;

@@ -335,12 +335,95 @@ OG_API void og_query_abort(og_query *q) { if (q) q->aborted = 1; }
 
 } /* extern "C" */
 namespace {
-struct ScratchSet { std::vector<void *> ptrs; ~ScratchSet() { for (void *p : ptrs) cudaFree(p); } };
-template <class T> int salloc(ScratchSet &ss, T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) ss.ptrs.push_back(*p); return rc; }
+struct Plan { /* built once per query, reused by every og_query_run */
+    ChunkP ch; TileP tp; GroupP gp;
+    bool fused;
+};
+template <class T> int salloc(og_query *q, T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) q->scratch.push_back(*p); return rc; }
 
 template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP &ch, cudaStream_t st) {
     uint32_t n = ch.seg_end - ch.seg_begin;
     k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch);
+}
+
+int build_plan(og_query *q) {
+    og_shard *s = q->sh;
+    const QueryP &p = q->qp;
+    cudaStream_t st = q->stream;
+    int rc;
+    Plan *pl = new Plan;
+    memset(pl, 0, sizeof *pl);
+    q->plan = pl;
+    size_t cells_dense = (size_t)q->n_groups * p.n_buckets;
+    for (uint32_t c = 0; c < p.n_calls; c++) { /* dense accumulators (the result) */
+        bool sel = p.calls[c].func >= OG_AGG_MIN && !(p.multi && p.calls[c].func <= OG_AGG_MAX);
+        if ((rc = dalloc(&q->dense[c].val, cells_dense))) return rc;
+        if ((rc = dalloc(&q->dense[c].ok, cells_dense))) return rc;
+        if (sel && (rc = dalloc(&q->dense[c].tim, cells_dense))) return rc;
+    }
+    /* group CSR: series sorted by (group, series) */
+    std::vector<uint32_t> grp_begin(q->n_groups + 1, 0), grp_series(s->n_series);
+    if (q->desc.group_mode == OG_GROUP_MAP) {
+        for (uint32_t sr = 0; sr < s->n_series; sr++) grp_begin[q->series_group[sr] + 1]++;
+        for (uint32_t g = 0; g < q->n_groups; g++) grp_begin[g + 1] += grp_begin[g];
+        std::vector<uint32_t> cur(grp_begin.begin(), grp_begin.end() - 1);
+        for (uint32_t sr = 0; sr < s->n_series; sr++) grp_series[cur[q->series_group[sr]]++] = sr;
+    } else if (q->desc.group_mode == OG_GROUP_PER_SERIES) {
+        for (uint32_t g = 0; g <= q->n_groups; g++) grp_begin[g] = std::min(g, s->n_series);
+        std::iota(grp_series.begin(), grp_series.end(), 0u);
+    } else { grp_begin[1] = s->n_series; std::iota(grp_series.begin(), grp_series.end(), 0u); }
+    uint32_t *d_grp_begin, *d_grp_series;
+    if ((rc = salloc(q, &d_grp_begin, grp_begin.size()))) return rc;
+    if ((rc = salloc(q, &d_grp_series, grp_series.size()))) return rc;
+    if ((rc = salloc(q, &q->d_err, 2))) return rc;
+    CU(cudaMemcpyAsync(d_grp_begin, grp_begin.data(), grp_begin.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_grp_series, grp_series.data(), grp_series.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st)); /* the host vectors die with this frame */
+    pl->gp.grp_begin = d_grp_begin; pl->gp.grp_series = d_grp_series; pl->gp.n_groups = q->n_groups;
+    for (uint32_t c = 0; c < p.n_calls; c++) pl->gp.dense[c] = q->dense[c];
+
+    /* chunk plan: whole series per chunk, per-series cells bounded by a memory budget */
+    size_t cell_bytes_per_series = 0;
+    for (uint32_t c = 0; c < p.n_calls; c++) cell_bytes_per_series += (size_t)p.n_buckets * (9 + (p.calls[c].func >= OG_AGG_MIN ? 8 : 0));
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
+    q->chunk_series = (uint32_t)std::max<size_t>(1, std::min<size_t>(s->n_series, budget / std::max<size_t>(1, cell_bytes_per_series)));
+    uint32_t max_chunk_segs = 0;
+    for (uint32_t a = 0; a < s->n_series; a += q->chunk_series) {
+        uint32_t b = std::min(s->n_series, a + q->chunk_series);
+        max_chunk_segs = std::max(max_chunk_segs, s->h_series_seg_begin[b] - s->h_series_seg_begin[a]);
+    }
+    ChunkP &ch = pl->ch;
+    ch.err = q->d_err;
+    size_t chunk_cells = (size_t)q->chunk_series * p.n_buckets;
+    for (uint32_t c = 0; c < p.n_calls; c++) {
+        bool sel = p.calls[c].func >= OG_AGG_MIN;
+        if ((rc = salloc(q, &ch.cells[c].val, chunk_cells))) return rc;
+        if ((rc = salloc(q, &ch.cells[c].ok, chunk_cells))) return rc;
+        if (sel && (rc = salloc(q, &ch.cells[c].tim, chunk_cells))) return rc;
+        if ((rc = salloc(q, &ch.edges[c].val, 2 * (size_t)max_chunk_segs))) return rc;
+        if ((rc = salloc(q, &ch.edges[c].ok, 2 * (size_t)max_chunk_segs))) return rc;
+        if (sel && (rc = salloc(q, &ch.edges[c].tim, 2 * (size_t)max_chunk_segs))) return rc;
+    }
+    if ((rc = salloc(q, &ch.edge_bucket, 2 * (size_t)max_chunk_segs))) return rc;
+
+    pl->fused = p.n_cols == 1 && p.n_filter == 0 && !(q->desc.flags & OG_Q_NO_FUSED);
+    q->path_used = pl->fused ? 1 : 0;
+    if (!pl->fused) { /* generic path: L2-sized materialisation tile */
+        TileP &tp = pl->tp;
+        tp.R = std::max<uint32_t>(1, s->max_seg_rows);
+        size_t per_seg = (size_t)tp.R * (p.n_cols * 9 + 8 + 1);
+        q->tile_segs = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max<uint32_t>(1, max_chunk_segs), ((size_t)96 << 20) / per_seg));
+        for (uint32_t k = 0; k < p.n_cols; k++) {
+            if ((rc = salloc(q, &tp.vals[k], (size_t)q->tile_segs * tp.R))) return rc;
+            if ((rc = salloc(q, &tp.okb[k], (size_t)q->tile_segs * tp.R))) return rc;
+        }
+        if ((rc = salloc(q, &tp.times, (size_t)q->tile_segs * tp.R))) return rc;
+        if ((rc = salloc(q, &tp.keep, (size_t)q->tile_segs * tp.R))) return rc;
+    }
+    q->planned = true;
+    return OG_OK;
 }
 } // namespace
 extern "C" {
@@ -353,97 +436,31 @@ OG_API int og_query_run(og_query *q) {
     cudaStream_t st = q->stream;
     int rc;
     q->host_ready = false; q->next_group = 0; q->next_row = 0;
+    if (!q->planned) {
+        if (q->plan) { set_error("query plan failed earlier"); return OG_E_STATE; }
+        if ((rc = build_plan(q))) return rc;
+    }
+    Plan *pl = (Plan *)q->plan;
+    ChunkP ch = pl->ch; TileP tp = pl->tp; const GroupP &gp = pl->gp;
     size_t cells_dense = (size_t)q->n_groups * p.n_buckets;
-    /* dense accumulators */
-    for (uint32_t c = 0; c < p.n_calls; c++) {
-        bool sel = p.calls[c].func >= OG_AGG_MIN && !(p.multi && p.calls[c].func <= OG_AGG_MAX);
-        if (!q->dense[c].val) {
-            if ((rc = dalloc(&q->dense[c].val, cells_dense))) return rc;
-            if ((rc = dalloc(&q->dense[c].ok, cells_dense))) return rc;
-            if (sel && (rc = dalloc(&q->dense[c].tim, cells_dense))) return rc;
-        }
-    }
-    ScratchSet ss;
-    /* group CSR */
-    std::vector<uint32_t> grp_begin(q->n_groups + 1, 0), grp_series(s->n_series);
-    if (q->desc.group_mode == OG_GROUP_MAP) {
-        for (uint32_t sr = 0; sr < s->n_series; sr++) grp_begin[q->series_group[sr] + 1]++;
-        for (uint32_t g = 0; g < q->n_groups; g++) grp_begin[g + 1] += grp_begin[g];
-        std::vector<uint32_t> cur(grp_begin.begin(), grp_begin.end() - 1);
-        for (uint32_t sr = 0; sr < s->n_series; sr++) grp_series[cur[q->series_group[sr]]++] = sr;
-    } else if (q->desc.group_mode == OG_GROUP_PER_SERIES) {
-        for (uint32_t g = 0; g <= q->n_groups; g++) grp_begin[g] = std::min(g, s->n_series);
-        std::iota(grp_series.begin(), grp_series.end(), 0u);
-    } else { grp_begin[1] = s->n_series; std::iota(grp_series.begin(), grp_series.end(), 0u); }
-    uint32_t *d_grp_begin, *d_grp_series; int *d_err;
-    if ((rc = salloc(ss, &d_grp_begin, grp_begin.size()))) return rc;
-    if ((rc = salloc(ss, &d_grp_series, grp_series.size()))) return rc;
-    if ((rc = salloc(ss, &d_err, 2))) return rc;
-    CU(cudaMemcpyAsync(d_grp_begin, grp_begin.data(), grp_begin.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_grp_series, grp_series.data(), grp_series.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(d_err, 0, 8, st));
-    GroupP gp; memset(&gp, 0, sizeof gp);
-    gp.grp_begin = d_grp_begin; gp.grp_series = d_grp_series; gp.n_groups = q->n_groups;
-    for (uint32_t c = 0; c < p.n_calls; c++) gp.dense[c] = q->dense[c];
-
-    /* chunk plan: whole series, cells budget */
-    size_t cell_bytes_per_series = 0;
-    for (uint32_t c = 0; c < p.n_calls; c++) cell_bytes_per_series += (size_t)p.n_buckets * (9 + (p.calls[c].func >= OG_AGG_MIN ? 8 : 0));
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
-    uint32_t chunk_series = (uint32_t)std::max<size_t>(1, std::min<size_t>(s->n_series, budget / std::max<size_t>(1, cell_bytes_per_series)));
-    /* widest chunk in segments, for the edge arrays */
-    uint32_t max_chunk_segs = 0;
-    for (uint32_t a = 0; a < s->n_series; a += chunk_series) {
-        uint32_t b = std::min(s->n_series, a + chunk_series);
-        max_chunk_segs = std::max(max_chunk_segs, s->h_series_seg_begin[b] - s->h_series_seg_begin[a]);
-    }
-    ChunkP ch; memset(&ch, 0, sizeof ch);
-    ch.err = d_err;
-    size_t chunk_cells = (size_t)chunk_series * p.n_buckets;
-    for (uint32_t c = 0; c < p.n_calls; c++) {
-        bool sel = p.calls[c].func >= OG_AGG_MIN;
-        if ((rc = salloc(ss, &ch.cells[c].val, chunk_cells))) return rc;
-        if ((rc = salloc(ss, &ch.cells[c].ok, chunk_cells))) return rc;
-        if (sel && (rc = salloc(ss, &ch.cells[c].tim, chunk_cells))) return rc;
-        if ((rc = salloc(ss, &ch.edges[c].val, 2 * (size_t)max_chunk_segs))) return rc;
-        if ((rc = salloc(ss, &ch.edges[c].ok, 2 * (size_t)max_chunk_segs))) return rc;
-        if (sel && (rc = salloc(ss, &ch.edges[c].tim, 2 * (size_t)max_chunk_segs))) return rc;
-    }
-    if ((rc = salloc(ss, &ch.edge_bucket, 2 * (size_t)max_chunk_segs))) return rc;
-
-    bool fused = p.n_cols == 1 && p.n_filter == 0 && !(q->desc.flags & OG_Q_NO_FUSED);
-    q->path_used = fused ? 1 : 0;
-    /* generic path tile buffers */
-    TileP tp; memset(&tp, 0, sizeof tp);
-    uint32_t tile_segs = 0;
-    if (!fused) {
-        tp.R = std::max<uint32_t>(1, s->max_seg_rows);
-        size_t per_seg = (size_t)tp.R * (p.n_cols * 9 + 8 + 1);
-        tile_segs = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max<uint32_t>(1, max_chunk_segs), ((size_t)96 << 20) / per_seg));
-        for (uint32_t k = 0; k < p.n_cols; k++) {
-            if ((rc = salloc(ss, &tp.vals[k], (size_t)tile_segs * tp.R))) return rc;
-            if ((rc = salloc(ss, &tp.okb[k], (size_t)tile_segs * tp.R))) return rc;
-        }
-        if ((rc = salloc(ss, &tp.times, (size_t)tile_segs * tp.R))) return rc;
-        if ((rc = salloc(ss, &tp.keep, (size_t)tile_segs * tp.R))) return rc;
-    }
     DirP dir = make_dir(s);
-    uint32_t launches = 0;
+    uint32_t launches = 0, n_chunks = (s->n_series + q->chunk_series - 1) / q->chunk_series;
+    while (q->main_ev.size() < 2 * (size_t)n_chunks) { cudaEvent_t e; CU(cudaEventCreate(&e)); q->main_ev.push_back(e); }
+    CU(cudaMemsetAsync(q->d_err, 0, 8, st));
     CU(cudaEventRecord(q->ev0, st));
     k_init_dense<<<(unsigned)((cells_dense + 255) / 256), 256, 0, st>>>(p, gp); launches++;
-    uint64_t segs_scanned = 0;
-    for (uint32_t a = 0; a < s->n_series; a += chunk_series) {
+    uint64_t segs_scanned = 0; uint32_t ci = 0, chunks_run = 0;
+    for (uint32_t a = 0; a < s->n_series; a += q->chunk_series, ci++) {
         if (q->aborted) { cudaStreamSynchronize(st); set_error("query aborted"); return OG_E_ABORTED; }
-        uint32_t b = std::min(s->n_series, a + chunk_series);
+        uint32_t b = std::min(s->n_series, a + q->chunk_series);
         ch.series_begin = a; ch.series_end = b;
         ch.seg_begin = s->h_series_seg_begin[a]; ch.seg_end = s->h_series_seg_begin[b];
         uint32_t nseg = ch.seg_end - ch.seg_begin;
         if (nseg == 0) continue;
         segs_scanned += nseg;
         for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)(b - a) * p.n_buckets, st));
-        if (fused) {
+        CU(cudaEventRecord(q->main_ev[2 * chunks_run], st));
+        if (pl->fused) {
             switch (p.n_calls) {
             case 1: launch_fused<1>(dir, p, ch, st); break;
             case 2: launch_fused<2>(dir, p, ch, st); break;
@@ -456,17 +473,19 @@ OG_API int og_query_run(og_query *q) {
             }
             launches++;
         } else {
-            for (uint32_t t0 = ch.seg_begin; t0 < ch.seg_end; t0 += tile_segs) {
-                tp.tile_begin = t0; tp.tile_end = std::min(ch.seg_end, t0 + tile_segs);
+            for (uint32_t t0 = ch.seg_begin; t0 < ch.seg_end; t0 += q->tile_segs) {
+                tp.tile_begin = t0; tp.tile_end = std::min(ch.seg_end, t0 + q->tile_segs);
                 uint32_t n = tp.tile_end - tp.tile_begin;
                 dim3 g((n + 127) / 128, p.n_cols + 1);
-                k_decode_tile<<<g, 128, 0, st>>>(dir, p, tp, d_err);
+                k_decode_tile<<<g, 128, 0, st>>>(dir, p, tp, q->d_err);
                 size_t rows_total = (size_t)n * tp.R;
                 k_filter_tile<<<(unsigned)((rows_total + 255) / 256), 256, 0, st>>>(dir, p, tp);
                 k_window_reduce<<<(n * 32 + 127) / 128, 128, 0, st>>>(dir, p, tp, ch);
                 launches += 3;
             }
         }
+        CU(cudaEventRecord(q->main_ev[2 * chunks_run + 1], st));
+        chunks_run++;
         k_fix_edges<<<(nseg + 127) / 128, 128, 0, st>>>(dir, p, ch);
         k_merge_groups<<<(unsigned)((cells_dense + 127) / 128), 128, 0, st>>>(p, ch, gp);
         launches += 2;
@@ -475,16 +494,17 @@ OG_API int og_query_run(og_query *q) {
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     int err[2];
-    CU(cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(err, q->d_err, 8, cudaMemcpyDeviceToHost));
     if (err[0]) { set_error("segment %d failed to decode (device code %d)", err[1], err[0]); return map_dev_err(err[0]); }
     float ms = 0; cudaEventElapsedTime(&ms, q->ev0, q->ev1);
+    double main_ms = 0;
+    for (uint32_t i = 0; i < chunks_run; i++) { float m = 0; cudaEventElapsedTime(&m, q->main_ev[2 * i], q->main_ev[2 * i + 1]); main_ms += m; }
     og_stats &stt = q->stats;
+    uint64_t keep_pb = stt.page_bytes, keep_rows = stt.rows_decoded, keep_segs = stt.segments_scanned; /* directory sums do not change between runs */
     memset(&stt, 0, sizeof stt);
-    stt.kernel_ms = ms; stt.kernel_launches = launches; stt.segments_scanned = segs_scanned;
-    stt.rows_decoded = s->n_rows; /* every segment overlapping the range is decoded whole; pruned segments are counted out below */
-    /* page bytes of the columns this query touched + time pages */
-    stt.page_bytes = 0; /* filled lazily by og_query_stats from the directory (kept off the timed path) */
-    stt.dir_bytes = (uint64_t)s->n_segments * (8 + 4) * (p.n_cols + 1) + (uint64_t)s->n_segments * (4 + 4 + 16);
+    stt.kernel_ms = ms; stt.main_kernel_ms = main_ms; stt.kernel_launches = launches; stt.path = q->path_used;
+    stt.page_bytes = keep_pb; stt.rows_decoded = keep_pb ? keep_rows : s->n_rows; stt.segments_scanned = keep_pb ? keep_segs : segs_scanned;
+    stt.dir_bytes = (uint64_t)segs_scanned * 32; /* SURVEY §8d accounting: 32 B of directory per scanned segment */
     stt.out_bytes = 0;
     for (uint32_t c = 0; c < p.n_calls; c++) stt.out_bytes += cells_dense * (9 + (q->dense[c].tim ? 8 : 0));
     q->ran = true;
@@ -495,7 +515,8 @@ OG_API int og_query_dense(og_query *q, og_dense_view *out) {
     if (!q || !out) return OG_E_INVAL;
     if (!q->ran) { set_error("og_query_dense before og_query_run"); return OG_E_STATE; }
     const QueryP &p = q->qp;
-    out->n_groups = q->n_groups; out->n_buckets = p.n_buckets; out->start = p.start; out->interval = q->desc.interval ? p.interval : 0;
+    /* without GROUP BY time() the single interval row carries time 0 (BuildEmptyIntervalRec !hasInterval, record.go:1328-1331) */
+    out->n_groups = q->n_groups; out->n_buckets = p.n_buckets; out->start = q->desc.interval ? p.start : 0; out->interval = q->desc.interval ? p.interval : 0;
     out->n_cols = p.n_calls;
     for (uint32_t c = 0; c < p.n_calls; c++) {
         q->dense_cols[c].values = q->dense[c].val; q->dense_cols[c].valid = q->dense[c].ok; q->dense_cols[c].times = q->dense[c].tim;
@@ -689,7 +710,7 @@ OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out)
     CU(cudaSetDevice(s->device));
     uint32_t R = std::max<uint32_t>(1, s->max_seg_rows);
     size_t ncol1 = (size_t)s->n_columns + 1;
-    size_t val_stride = (size_t)R * 8, bm_stride = (R + 7) / 8;
+    size_t val_stride = (size_t)R * 8, bm_stride = (((size_t)R + 7) / 8 + 7) & ~(size_t)7;
     size_t need = ncol1 * (val_stride + bm_stride + 16);
     if (s->d_seg_buf_bytes < need) {
         if (s->d_seg_buf) cudaFree(s->d_seg_buf);

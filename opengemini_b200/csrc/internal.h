@@ -102,4 +102,10 @@ struct og_query {
     std::vector<int64_t> rv_times;
     std::vector<og_colval_view> rv_cols;
     int path_used = 0; /* 0 generic tile path, 1 fused */
+    /* execution plan + scratch, built by the first og_query_run and reused by later runs */
+    bool planned = false;
+    uint32_t chunk_series = 0, tile_segs = 0;
+    int *d_err = nullptr;
+    void *plan = nullptr; /* ogpu::Plan (agg_kernels.cuh types) */
+    std::vector<cudaEvent_t> main_ev; /* event pairs around the dominant decode+reduce kernels */
 };

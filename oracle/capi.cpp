@@ -87,8 +87,13 @@ OGO_API void ogo_window(int64_t interval, int64_t offset, int64_t tmin, int64_t 
 }
 
 /* ---- synthetic shard ---- */
+OGO_API void *ogo_synth_build_mt(const og_synth_desc *d, int threads, int *status) {
+    HostShard *h = new HostShard; int rc = build_synth_shard(*d, *h, threads); if (status) *status = rc;
+    if (rc != E_OK) { delete h; return nullptr; }
+    return h;
+}
 OGO_API void *ogo_synth_build(const og_synth_desc *d, int *status) {
-    HostShard *h = new HostShard; int rc = build_synth_shard(*d, *h); if (status) *status = rc;
+    HostShard *h = new HostShard; int rc = build_synth_shard(*d, *h, 1); if (status) *status = rc;
     if (rc != E_OK) { delete h; return nullptr; }
     return h;
 }

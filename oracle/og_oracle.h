@@ -198,7 +198,7 @@ struct HostShard {
     std::vector<og_column_desc> col_descs;
     og_shard_desc desc() ;
 };
-int build_synth_shard(const og_synth_desc &d, HostShard &out);
+int build_synth_shard(const og_synth_desc &d, HostShard &out, int threads = 1);
 
 } // namespace ogo
 

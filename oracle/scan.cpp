@@ -53,7 +53,11 @@ struct SeriesFeeder { /* plays the role of fileCursor/Location for one series */
     std::vector<int> cols;          /* shard field columns materialised, in in_schema order */
     std::vector<Field> in_schema;
     uint32_t seg, seg_end;
-    Record ring[3]; int ring_idx = 0; /* tsmMerge ring = 3 (engine/iterators.go:61-70) */
+    Record ring[4]; /* record pool: the two most recently returned records stay untouched (the aggregate cursor holds the
+                       current record while it peeks the next one; CircularRecordPool rings, engine/iterators.go:61-70) */
+    int held[2] = {-1, -1};
+    int pick(int other) const { for (int i = 0; i < 4; i++) if (i != held[0] && i != held[1] && i != other) return i; return 0; }
+    const Record *give(int slot) { held[0] = held[1]; held[1] = slot; return &ring[slot]; }
     uint64_t rows_decoded = 0, segments = 0, page_bytes = 0;
     int error = 0;
 
@@ -61,7 +65,8 @@ struct SeriesFeeder { /* plays the role of fileCursor/Location for one series */
         while (seg < seg_end) {
             uint32_t s = seg++;
             if (sh->seg_tmax[s] < q->tmin || sh->seg_tmin[s] > q->tmax) continue; /* tr.Overlaps location.go:276-280 */
-            Record &r = ring[ring_idx]; ring_idx = (ring_idx + 1) % 3;
+            int r_slot = pick(-1);
+            Record &r = ring[r_slot];
             r.reset();
             ColVal &tc = r.cols.back();
             int rc = decode_time_page(sh->data + sh->time_page_off[s], sh->time_page_len[s], tc);
@@ -84,7 +89,11 @@ struct SeriesFeeder { /* plays the role of fileCursor/Location for one series */
             /* FilterByTime reader.go:754-771 and FilterByField :895-974, as one row mask + gather (genRecByRowNumbers :809-860) */
             const int64_t *t = tc.integers();
             bool all_in = q->tmin <= t[0] && t[rows - 1] <= q->tmax;
-            if (all_in && q->n_filter == 0) return &r;
+            /* KickNilRow (lib/record/record.go:1188-1240, called at file_cursor.go:293,334,349 after the filters): rows whose
+               field columns are all null are dropped; fast path when any column has no nulls */
+            bool may_kick = true;
+            for (size_t k = 0; k + 1 < r.cols.size(); k++) if (r.cols[k].len != 0 && r.cols[k].nil_count == 0) may_kick = false;
+            if (all_in && q->n_filter == 0 && !may_kick) return give(r_slot);
             std::vector<uint8_t> keep((size_t)rows, 1);
             if (!all_in) for (int i = 0; i < rows; i++) keep[i] = t[i] >= q->tmin && t[i] <= q->tmax;
             if (q->n_filter) {
@@ -114,8 +123,16 @@ struct SeriesFeeder { /* plays the role of fileCursor/Location for one series */
                 }
                 for (int i = 0; i < rows; i++) keep[i] &= stack.back()[i];
             }
+            if (may_kick)
+                for (int i = 0; i < rows; i++) {
+                    if (!keep[i]) continue;
+                    bool all_nil = true;
+                    for (size_t k = 0; k + 1 < r.cols.size(); k++) all_nil = all_nil && r.cols[k].is_nil(i);
+                    if (all_nil) keep[i] = 0;
+                }
             /* gather surviving rows */
-            Record &o = ring[ring_idx]; ring_idx = (ring_idx + 1) % 3;
+            int o_slot = pick(r_slot);
+            Record &o = ring[o_slot];
             o.reset();
             for (size_t k = 0; k < r.cols.size(); k++) {
                 const ColVal &c = r.cols[k];
@@ -133,7 +150,7 @@ struct SeriesFeeder { /* plays the role of fileCursor/Location for one series */
                 }
             }
             if (o.row_nums() == 0) continue;
-            return &o;
+            return give(o_slot);
         }
         return nullptr;
     }
@@ -278,7 +295,7 @@ og_shard_desc HostShard::desc() {
     return d;
 }
 
-int build_synth_shard(const og_synth_desc &d, HostShard &out) {
+int build_synth_shard(const og_synth_desc &d, HostShard &out, int threads) {
     uint32_t rps = d.rows_per_segment ? d.rows_per_segment : 1000;
     uint32_t segs_per_series = (d.rows_per_series + rps - 1) / rps;
     uint32_t nseg = d.n_series * segs_per_series;
@@ -288,24 +305,33 @@ int build_synth_shard(const og_synth_desc &d, HostShard &out) {
     out.page_len.assign(d.n_columns + 1, std::vector<uint32_t>(nseg));
     out.col_types.resize(d.n_columns); out.col_names.resize(d.n_columns);
     for (uint32_t c = 0; c < d.n_columns; c++) { out.col_types[c] = d.columns[c].type; out.col_names[c] = "f" + std::to_string(c); }
-    std::vector<int64_t> times(rps);
     /* layout mirrors a TSSP chunk: per series, each field column's pages back to back, then the time pages
-       (chunkdata_builder_ts.go:36-82); the 4-byte per-column CRC slots are kept so offsets look like a real file */
-    for (uint32_t s = 0; s < d.n_series; s++) {
+       (chunkdata_builder_ts.go:36-82); the 4-byte per-column CRC slots are kept so offsets look like a real file.
+       Series ranges are encoded by worker threads into private buffers and concatenated in series order. */
+    if (threads < 1) threads = 1;
+    if ((uint32_t)threads > d.n_series) threads = (int)d.n_series;
+    std::vector<Bytes> bufs((size_t)threads);
+    std::vector<int> rcs((size_t)threads, E_OK);
+    auto range_of = [&](int t, uint32_t *a, uint32_t *b) { *a = (uint32_t)((uint64_t)d.n_series * t / threads); *b = (uint32_t)((uint64_t)d.n_series * (t + 1) / threads); };
+    auto build_range = [&](int tid) -> int {
+    uint32_t s_a, s_b; range_of(tid, &s_a, &s_b);
+    Bytes &data = bufs[(size_t)tid];
+    std::vector<int64_t> times(rps);
+    for (uint32_t s = s_a; s < s_b; s++) {
         out.sids[s] = (uint64_t)s + 1;
         out.series_seg_begin[s] = s * segs_per_series;
         for (uint32_t c = 0; c <= d.n_columns; c++) {
-            out.data.insert(out.data.end(), 4, 0); /* crc32 placeholder (not verified by the attached read path) */
+            data.insert(data.end(), 4, 0); /* crc32 placeholder (not verified by the attached read path) */
             for (uint32_t g = 0; g < segs_per_series; g++) {
                 uint32_t seg = s * segs_per_series + g;
                 uint64_t row0 = (uint64_t)g * rps;
                 uint32_t n = (uint32_t)std::min<uint64_t>(rps, d.rows_per_series - row0);
-                uint64_t off = out.data.size();
+                uint64_t off = data.size();
                 int rc;
                 if (c == d.n_columns) {
                     for (uint32_t i = 0; i < n; i++) times[i] = d.t0 + (int64_t)(row0 + i) * d.dt;
                     out.seg_tmin[seg] = times[0]; out.seg_tmax[seg] = times[n - 1];
-                    rc = encode_time_page(times.data(), n, out.data);
+                    rc = encode_time_page(times.data(), n, data);
                 } else {
                     const og_synth_column &sc = d.columns[c];
                     ColVal cv;
@@ -325,13 +351,33 @@ int build_synth_shard(const og_synth_desc &d, HostShard &out) {
                             if (nil) cv.append_null(OG_TYPE_BOOL, false); else cv.append_boolean(og_synth_bool(d.seed, c, s, row) != 0); break;
                         }
                     }
-                    rc = encode_field_page(cv, sc.type, out.data);
+                    rc = encode_field_page(cv, sc.type, data);
                 }
                 if (rc != E_OK) return rc;
                 out.page_off[c][seg] = off;
-                out.page_len[c][seg] = (uint32_t)(out.data.size() - off);
+                out.page_len[c][seg] = (uint32_t)(data.size() - off);
             }
         }
+    }
+    return E_OK;
+    };
+    if (threads == 1) rcs[0] = build_range(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++) th.emplace_back([&, t]() { rcs[(size_t)t] = build_range(t); });
+        for (auto &t : th) t.join();
+    }
+    for (int rc : rcs) if (rc != E_OK) return rc;
+    uint64_t total = 0;
+    std::vector<uint64_t> base((size_t)threads);
+    for (int t = 0; t < threads; t++) { base[(size_t)t] = total; total += bufs[(size_t)t].size(); }
+    out.data.resize(total);
+    for (int t = 0; t < threads; t++) {
+        if (!bufs[(size_t)t].empty()) memcpy(out.data.data() + base[(size_t)t], bufs[(size_t)t].data(), bufs[(size_t)t].size());
+        uint32_t s_a, s_b; range_of(t, &s_a, &s_b);
+        for (uint32_t c = 0; c <= d.n_columns; c++)
+            for (uint32_t seg = s_a * segs_per_series; seg < s_b * segs_per_series; seg++) out.page_off[c][seg] += base[(size_t)t];
+        Bytes().swap(bufs[(size_t)t]);
     }
     out.series_seg_begin[d.n_series] = nseg;
     return E_OK;

@@ -186,7 +186,7 @@ def test_time_codecs_decode(shape):
         t = np.array([T0, T0 + 17], np.int64)
     else:
         t = np.array([T0 + 5], np.int64)
-    v = np.arange(t.size, dtype=np.float64) * 1.5 + 0.25
+    v = 100 + rng.random(t.size)  # full-mantissa values: Gorilla (few-decimal values would route to Snappy, float.go:206)
     page = oracle.field_page_encode(L.TYPE_FLOAT, v)
     sh = _one_segment_shard(L.TYPE_FLOAT, page, oracle.time_page_encode(t), t)
     rec = sh.decode_segment(0)
@@ -320,22 +320,24 @@ def test_where_filters(agg_shard):
 
 
 def test_nan_and_tie_semantics():
-    """NaN handling (strict compares, sticky first NaN) and tie-breaks must follow the reducers exactly."""
-    n = 1000
+    """NaN handling (strict compares, sticky first NaN of a record window) and tie-breaks must follow the reducers exactly.
+    NaN can only reach a page through the raw/Snappy routes (FloatArrayEncodeAll rejects it), so the shard is built from
+    4-row segments (n <= 4 -> floatCompressedNull, float.go:26,96): windows then span many records, which is exactly where
+    the record-boundary-dependent NaN behaviour of the reducers shows."""
+    n, nsegs, nser = 4, 40, 6
     rng = np.random.default_rng(21)
     series = []
-    for s in range(4):
-        v = np.round(rng.random(3 * n) * 4) / 4  # many ties
-        v[rng.integers(0, 3 * n, 40)] = np.nan
+    for s in range(nser):
+        v = np.round(rng.random(n * nsegs) * 4) / 4  # many ties
+        v[rng.integers(0, n * nsegs, 25)] = np.nan
         if s == 1:
-            v[0] = np.nan  # window that starts with NaN
-            v[n] = np.nan  # record (segment) that starts with NaN inside a window spanning two segments
+            v[0] = np.nan      # window that starts with NaN
+            v[8] = np.nan      # a record that starts with NaN inside a window spanning several records
         series.append(v)
     pages, tpages, tmins, tmaxs = [], [], [], []
-    for s in range(4):
-        for g in range(3):
-            seg = series[s][g * n:(g + 1) * n]
-            pages.append(oracle.field_page_encode(L.TYPE_FLOAT, seg))
+    for s in range(nser):
+        for g in range(nsegs):
+            pages.append(oracle.field_page_encode(L.TYPE_FLOAT, series[s][g * n:(g + 1) * n]))
             t = T0 + (np.arange(n, dtype=np.int64) + g * n) * SEC
             tpages.append(oracle.time_page_encode(t)); tmins.append(t[0]); tmaxs.append(t[-1])
     blob, offs, lens = [], [], []
@@ -343,16 +345,19 @@ def test_nan_and_tie_semantics():
     for p in pages + tpages:
         offs.append(pos); lens.append(p.size); blob.append(p); pos += p.size
     data = np.concatenate(blob)
-    nseg = 12
-    sh = Shard.open(data, [1, 2, 3, 4], [0, 3, 6, 9, 12], tmins, tmaxs, [("v", L.TYPE_FLOAT, offs[:nseg], lens[:nseg])], offs[nseg:], lens[nseg:])
+    nseg = nser * nsegs
+    sh = Shard.open(data, np.arange(1, nser + 1), np.arange(0, nseg + 1, nsegs), tmins, tmaxs,
+                    [("v", L.TYPE_FLOAT, offs[:nseg], lens[:nseg])], offs[nseg:], lens[nseg:])
     ex = sh.export()
     sd = oracle.shard_desc_from_export(ex)
+    tmax = T0 + n * nsegs * SEC
     for flags in (0, L.Q_NO_FUSED):
-        for iv in (60 * SEC, 700 * SEC):
+        for iv in (7 * SEC, 60 * SEC, 0):
             for f in ALL6:
-                run_both(sh, sd, [(f, 0)], iv, T0, T0 + 3 * n * SEC, f"nan {f} iv={iv}", flags=flags)
-            run_both(sh, sd, [(f, 0) for f in ALL6], iv, T0, T0 + 3 * n * SEC, "nan multi", flags=flags)
-            run_both(sh, sd, [("max", 0)], iv, T0, T0 + 3 * n * SEC, "nan max per series", flags=flags, group="series")
+                run_both(sh, sd, [(f, 0)], iv, T0, tmax, f"nan {f} iv={iv}", flags=flags)
+            run_both(sh, sd, [(f, 0) for f in ALL6], iv, T0, tmax, "nan multi", flags=flags)
+            run_both(sh, sd, [("max", 0)], iv, T0, tmax, "nan max per series", flags=flags, group="series")
+            run_both(sh, sd, [("min", 0)], iv, T0 + 3 * SEC, tmax - 5 * SEC, "nan min mid-range", flags=flags)
     sh.close()
 
 
