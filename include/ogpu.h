@@ -90,6 +90,10 @@ enum {
                                    sequential merge, lib/record/reccord_functions.go:730-733) instead of chunked order */
     ,
     OG_Q_NO_FUSED = 1u << 1 /* force the generic materialise-tile path even when the fused kernel is eligible (testing / A-B) */
+    ,
+    OG_Q_NO_FAST = 1u << 2 /* fused path, but without the specialised Gorilla/const-delta kernel (testing / A-B) */
+    ,
+    OG_Q_STAGE_TMA = 1u << 3 /* fast kernel: stage pages with per-lane cp.async.bulk copies instead of warp-cooperative loads (A-B) */
 };
 
 typedef struct og_query_desc {
@@ -117,7 +121,8 @@ typedef struct og_column_desc {
 } og_column_desc;
 
 enum {
-    OG_SHARD_DEVICE_DATA = 1u << 0 /* `data` is a device pointer owned by the caller for the shard's lifetime (zero-copy) */
+    OG_SHARD_DEVICE_DATA = 1u << 0 /* `data` is a device pointer owned by the caller for the shard's lifetime (zero-copy);
+                                      the allocation must extend >= 1024 readable bytes past data_len (whole-chunk TMA copies) */
 };
 
 typedef struct og_shard_desc {

@@ -19,6 +19,8 @@ OP_LT, OP_LTE, OP_GT, OP_GTE, OP_EQ, OP_NEQ = 0, 1, 2, 3, 4, 5
 GROUP_ALL, GROUP_PER_SERIES, GROUP_MAP = 0, 1, 2
 Q_STRICT_ORDER = 1
 Q_NO_FUSED = 2
+Q_NO_FAST = 4
+Q_STAGE_TMA = 8
 SYNTH_F_HI, SYNTH_F_LO, SYNTH_INT_WALK, SYNTH_BOOL = 0, 1, 2, 3
 SHARD_DEVICE_DATA = 1
 

@@ -308,13 +308,29 @@ __global__ void k_merge_groups(QueryP q, ChunkP ch, GroupP gp) {
     for (uint32_t c = 0; c < q.n_calls; c++) {
         const CallP &cp = q.calls[c];
         Part acc = load_part(gp.dense[c], idx);
-        for (uint32_t i = lo; i < hi; i++) {
-            uint32_t s = gp.grp_series[i];
-            if (s >= ch.series_end) break;
-            size_t ci = (size_t)(s - ch.series_begin) * q.n_buckets + b;
-            if (!ch.cells[c].ok[ci]) continue;
-            Part p = load_part(ch.cells[c], ci);
-            group_update(cp.func, cp.out_type == OG_TYPE_INT && cp.func == OG_AGG_COUNT ? OG_TYPE_INT : cp.type, q.multi != 0, acc, p);
+        const Tri cells = ch.cells[c];
+        /* The fold is strictly sequential in series order (that is the reference's order, reccord_functions.go:730-733),
+         * but the loads do not depend on it: fetch a batch of U partials first, so each thread keeps U independent
+         * loads in flight (16,667 bucket threads alone cannot hide DRAM latency). */
+        constexpr int U = 8;
+        for (uint32_t i = lo; i < hi; i += U) {
+            uint32_t okv[U]; uint64_t vv[U]; int64_t tt[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                uint32_t ii = i + u;
+                uint32_t s = ii < hi ? gp.grp_series[ii] : 0xffffffffu;
+                bool in = s < ch.series_end;
+                size_t ci = in ? (size_t)(s - ch.series_begin) * q.n_buckets + b : 0;
+                okv[u] = in ? cells.ok[ci] : 0;
+                vv[u] = in ? cells.val[ci] : 0;
+                tt[u] = (in && cells.tim) ? cells.tim[ci] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (!okv[u]) continue;
+                Part p; p.ok = 1; p.v = vv[u]; p.t = tt[u];
+                group_update(cp.func, cp.out_type == OG_TYPE_INT && cp.func == OG_AGG_COUNT ? OG_TYPE_INT : cp.type, q.multi != 0, acc, p);
+            }
         }
         store_part(gp.dense[c], idx, acc);
     }

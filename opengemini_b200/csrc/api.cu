@@ -10,6 +10,7 @@
 
 #include "agg_kernels.cuh"
 #include "fused.cuh"
+#include "fused_fast.cuh"
 #include "internal.h"
 
 namespace ogpu {
@@ -177,9 +178,9 @@ OG_API int og_shard_open(const og_shard_desc *d, og_shard **out) {
 #define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = cuda_fail(e_, #x, __FILE__, __LINE__); og_shard_close(s); return rc; } } while (0)
     if (d->flags & OG_SHARD_DEVICE_DATA) { s->d_data = (uint8_t *)d->data; s->owns_data = false; }
     else {
-        TRY(dalloc(&s->d_data, d->data_len + 32)); /* 16+ bytes of tail padding for the word-wise unaligned loads */
+        TRY(dalloc(&s->d_data, d->data_len + 1024)); /* tail padding: word-wise unaligned loads and whole-chunk TMA copies read past the last page */
         TRYCU(cudaMemcpy(s->d_data, d->data, d->data_len, cudaMemcpyHostToDevice));
-        TRYCU(cudaMemset(s->d_data + d->data_len, 0, 32));
+        TRYCU(cudaMemset(s->d_data + d->data_len, 0, 1024));
     }
     TRY(dalloc(&s->d_series_seg_begin, (size_t)d->n_series + 1));
     TRY(dalloc(&s->d_tmin, nseg)); TRY(dalloc(&s->d_tmax, nseg));
@@ -338,12 +339,39 @@ namespace {
 struct Plan { /* built once per query, reused by every og_query_run */
     ChunkP ch; TileP tp; GroupP gp;
     bool fused;
+    uint8_t *cls;   /* per-segment class (SEG_FAST / SEG_GENERAL) when the fast Gorilla kernel applies, else nullptr */
+    int fm; bool times;
 };
 template <class T> int salloc(og_query *q, T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) q->scratch.push_back(*p); return rc; }
 
-template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP &ch, cudaStream_t st) {
+template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
     uint32_t n = ch.seg_end - ch.seg_begin;
-    k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch);
+    k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch, cls);
+}
+template <int FM, bool TIMES> void launch_fast_t(int stage, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
+    uint32_t n = ch.seg_end - ch.seg_begin;
+    dim3 grid((n + OG_FAST_THREADS - 1) / OG_FAST_THREADS), block(OG_FAST_THREADS);
+    (void)stage;
+    k_fused_fast<FM, TIMES><<<grid, block, 0, st>>>(d, p, ch, cls);
+}
+/* a handful of aggregate-set specialisations; anything else runs the all-aggregates instance */
+void launch_fast(int fm, bool times, int stage, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
+    if (!times) {
+        switch (fm) {
+        case FM_SUM | FM_COUNT: return launch_fast_t<FM_SUM | FM_COUNT, false>(stage, d, p, ch, cls, st);
+        case FM_SUM | FM_COUNT | FM_MAX: return launch_fast_t<FM_SUM | FM_COUNT | FM_MAX, false>(stage, d, p, ch, cls, st);
+        case FM_SUM | FM_COUNT | FM_MIN | FM_MAX: return launch_fast_t<FM_SUM | FM_COUNT | FM_MIN | FM_MAX, false>(stage, d, p, ch, cls, st);
+        case FM_COUNT: return launch_fast_t<FM_COUNT, false>(stage, d, p, ch, cls, st);
+        default: break;
+        }
+    } else {
+        switch (fm) {
+        case FM_MAX | FM_COUNT: return launch_fast_t<FM_MAX | FM_COUNT, true>(stage, d, p, ch, cls, st);
+        case FM_MIN | FM_COUNT: return launch_fast_t<FM_MIN | FM_COUNT, true>(stage, d, p, ch, cls, st);
+        default: break;
+        }
+    }
+    return launch_fast_t<63, true>(stage, d, p, ch, cls, st);
 }
 
 int build_plan(og_query *q) {
@@ -410,6 +438,19 @@ int build_plan(og_query *q) {
 
     pl->fused = p.n_cols == 1 && p.n_filter == 0 && !(q->desc.flags & OG_Q_NO_FUSED);
     q->path_used = pl->fused ? 1 : 0;
+    if (pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments) {
+        /* classify once: which segments the specialised Gorilla kernel takes (the rest go to k_fused_segment) */
+        if ((rc = salloc(q, &pl->cls, (size_t)s->n_segments))) return rc;
+        k_classify<<<(s->n_segments + 255) / 256, 256, 0, st>>>(make_dir(s), p, pl->cls);
+        CU(cudaGetLastError());
+        pl->fm = 0; pl->times = false;
+        for (uint32_t c = 0; c < p.n_calls; c++) {
+            pl->fm |= 1 << (p.calls[c].func - 1);
+            if (p.calls[c].func >= OG_AGG_MIN && !(p.multi && p.calls[c].func <= OG_AGG_MAX)) pl->times = true;
+        }
+        pl->fm |= FM_COUNT; /* the row count also is the validity of every partial */
+        q->path_used = 2;
+    }
     if (!pl->fused) { /* generic path: L2-sized materialisation tile */
         TileP &tp = pl->tp;
         tp.R = std::max<uint32_t>(1, s->max_seg_rows);
@@ -461,15 +502,16 @@ OG_API int og_query_run(og_query *q) {
         for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)(b - a) * p.n_buckets, st));
         CU(cudaEventRecord(q->main_ev[2 * chunks_run], st));
         if (pl->fused) {
+            if (pl->cls) { launch_fast(pl->fm, pl->times, 0, dir, p, ch, pl->cls, st); launches++; }
             switch (p.n_calls) {
-            case 1: launch_fused<1>(dir, p, ch, st); break;
-            case 2: launch_fused<2>(dir, p, ch, st); break;
-            case 3: launch_fused<3>(dir, p, ch, st); break;
-            case 4: launch_fused<4>(dir, p, ch, st); break;
-            case 5: launch_fused<5>(dir, p, ch, st); break;
-            case 6: launch_fused<6>(dir, p, ch, st); break;
-            case 7: launch_fused<7>(dir, p, ch, st); break;
-            default: launch_fused<8>(dir, p, ch, st); break;
+            case 1: launch_fused<1>(dir, p, ch, pl->cls, st); break;
+            case 2: launch_fused<2>(dir, p, ch, pl->cls, st); break;
+            case 3: launch_fused<3>(dir, p, ch, pl->cls, st); break;
+            case 4: launch_fused<4>(dir, p, ch, pl->cls, st); break;
+            case 5: launch_fused<5>(dir, p, ch, pl->cls, st); break;
+            case 6: launch_fused<6>(dir, p, ch, pl->cls, st); break;
+            case 7: launch_fused<7>(dir, p, ch, pl->cls, st); break;
+            default: launch_fused<8>(dir, p, ch, pl->cls, st); break;
             }
             launches++;
         } else {

@@ -520,7 +520,7 @@ OG_API int og_shard_synth(const og_synth_desc *dd, og_shard **out) {
         est += (uint64_t)(avg[c] * 1.02 * nseg) + (1u << 20);
     }
     s->data_len = est;
-    STRY(dalloc2(&s->d_data, est + 64));
+    STRY(dalloc2(&s->d_data, est + 1024));
     s->owns_data = true;
     uint64_t base = 0;
     for (uint32_t c = 0; c < ncol1; c++) {
@@ -535,7 +535,7 @@ OG_API int og_shard_synth(const og_synth_desc *dd, og_shard **out) {
     int fl = 0;
     STRYCU(cudaMemcpy(&fl, flags, 4, cudaMemcpyDeviceToHost));
     if (fl & 16) { set_error("synthetic blob overflow"); og_shard_close(s); return OG_E_NOMEM; }
-    STRYCU(cudaMemset(s->d_data + base, 0, std::min<uint64_t>(64, est + 64 - base)));
+    STRYCU(cudaMemset(s->d_data + base, 0, std::min<uint64_t>(1024, est + 1024 - base)));
     s->data_len = base;
     STRY(shard_finalize(s));
     *out = s;

@@ -91,9 +91,10 @@ struct FusedState {
 };
 
 template <int NC>
-__global__ void __launch_bounds__(128) k_fused_segment(DirP d, QueryP q, ChunkP ch) {
+__global__ void __launch_bounds__(128) k_fused_segment(DirP d, QueryP q, ChunkP ch, const uint8_t *cls) {
     uint32_t seg = ch.seg_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= ch.seg_end) return;
+    if (cls && cls[seg] == 1) return; /* SEG_FAST: handled by k_fused_fast */
     size_t e = 2 * (size_t)(seg - ch.seg_begin);
     uint32_t rows = d.seg_rows[seg];
     /* segment pruning by directory time range (location.go:276-280) */
