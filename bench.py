@@ -151,54 +151,9 @@ def run_reference(a):
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
 def cross_shard_merge(torch, dist, q, dense, world):
-    """configs[3]: NCCL merge of the dense bucket arrays.  sum/count: all-reduce; selectors: all-gather + ordered fold
-    (og_query_merge_dense keeps the reference's tie-breaks, lib/record/reccord_functions.go:482-494)."""
-    from opengemini_b200 import _lib as L
-    sel_cols = []
-    for i, c in enumerate(dense["cols"]):
-        if c["func"] in (L.AGG_SUM, L.AGG_COUNT):
-            dist.all_reduce(c["values"], op=dist.ReduceOp.SUM)
-            dist.all_reduce(c["valid"], op=dist.ReduceOp.MAX)
-        else:
-            sel_cols.append(i)
-    if not sel_cols:
-        return
-    gathered = {}
-    for i in sel_cols:
-        c = dense["cols"][i]
-        gv = [torch.empty_like(c["values"]) for _ in range(world)]
-        gk = [torch.empty_like(c["valid"]) for _ in range(world)]
-        dist.all_gather(gv, c["values"])
-        dist.all_gather(gk, c["valid"])
-        gt = None
-        if c["times"] is not None:
-            gt = [torch.empty_like(c["times"]) for _ in range(world)]
-            dist.all_gather(gt, c["times"])
-        gathered[i] = (gv, gk, gt)
-    # fold ranks 0..world-1 in rank order on every rank: start from rank 0's partial
-    for i in sel_cols:
-        c = dense["cols"][i]
-        gv, gk, gt = gathered[i]
-        c["values"].copy_(gv[0]); c["valid"].copy_(gk[0])
-        if gt is not None:
-            c["times"].copy_(gt[0])
-    torch.cuda.synchronize()
-    dv = q.dense_view()
-    for r in range(1, world):
-        cols = (L.DenseCol * dv.n_cols)()
-        for i in range(dv.n_cols):
-            cols[i] = dv.cols[i]
-            if i in gathered:
-                gv, gk, gt = gathered[i]
-                cols[i].values, cols[i].valid = gv[r].data_ptr(), gk[r].data_ptr()
-                cols[i].times = gt[r].data_ptr() if gt is not None else None
-        other = L.DenseView(dv.n_groups, dv.n_buckets, dv.start, dv.interval, dv.n_cols, cols, None)
-        # sum/count columns were already all-reduced: give the fold an all-invalid partial for them
-        zero_ok = torch.zeros(dv.n_groups * dv.n_buckets, dtype=torch.uint8, device=dense["cols"][0]["valid"].device)
-        for i in range(dv.n_cols):
-            if i not in gathered:
-                cols[i].valid = zero_ok.data_ptr()
-        L.check(L.lib().og_query_merge_dense(q.h, C.byref(other)), "og_query_merge_dense")
+    """configs[3]: NCCL merge of the dense bucket arrays (opengemini_b200/shard_merge.py)."""
+    from opengemini_b200 import shard_merge
+    shard_merge.cross_shard_merge(torch, dist, dense["cols"], world, shard_merge.gpu_fold(torch, q))
 
 
 def run_ours(a):

@@ -257,9 +257,13 @@ OG_API void og_query_destroy(og_query *q) {
     delete q;
 }
 
-OG_API int og_query_create(og_shard *s, const og_query_desc *d, og_query **out) {
-    if (!s || !d || !out) { set_error("null argument"); return OG_E_INVAL; }
+OG_API int og_query_create(og_shard *s, const og_query_desc *d_in, og_query **out) {
+    if (!s || !d_in || !out) { set_error("null argument"); return OG_E_INVAL; }
     *out = nullptr;
+    /* influxql.MinTime/MaxTime (ast.go:92,102) bound every query range, so that EndTime+1 in Window() cannot overflow */
+    og_query_desc d_clamped = *d_in;
+    d_clamped.tmin = std::max(d_in->tmin, MIN_TIME); d_clamped.tmax = std::min(d_in->tmax, MAX_TIME);
+    const og_query_desc *d = &d_clamped;
     CU(cudaSetDevice(s->device));
     if (!d->ascending) { set_error("descending scans are not supported on the GPU path"); return OG_E_UNSUPPORTED; }
     if (d->n_calls == 0 || d->n_calls > OG_MAX_CALLS) { set_error("n_calls must be 1..%d", OG_MAX_CALLS); return OG_E_INVAL; }
@@ -309,9 +313,16 @@ OG_API int og_query_create(og_shard *s, const og_query_desc *d, og_query **out) 
     if (d->n_filter && sp != 1) { set_error("filter RPN does not reduce to one value"); delete q; return OG_E_INVAL; }
     p.n_filter = d->n_filter;
     /* bucket geometry: TimeWindowsInit (agg_tagset_cursor.go:1012-1027) over the query range (updateQueryTime :448-463) */
+    /* FileInfo.{Min,Max}Time is the file range intersected with the query range (fileLoopCursor.updateQueryTime :448-463),
+     * so open-ended queries (opt.StartTime/EndTime = Min/MaxTime) get a bounded interval record. */
+    int64_t gmin = std::max(d->tmin, s->tmin), gmax = std::min(d->tmax, s->tmax);
+    if (gmin > gmax) gmin = gmax = d->tmin; /* no overlap: one empty window */
     int64_t s0, e0, s1, e1;
-    window_of(d->interval, d->offset, d->tmin, d->tmax, d->tmin, &s0, &e0);
-    window_of(d->interval, d->offset, d->tmin, d->tmax, d->tmax + 1, &s1, &e1);
+    if (d->interval == 0) { s0 = gmin; e0 = gmax + 1; s1 = s0; e1 = e0; }
+    else {
+        window_of(d->interval, d->offset, d->tmin, d->tmax, gmin, &s0, &e0);
+        window_of(d->interval, d->offset, d->tmin, d->tmax, gmax + 1, &s1, &e1);
+    }
     p.tmin = d->tmin; p.tmax = d->tmax; p.start = s0; p.interval = e0 - s0;
     if (p.interval <= 0) { set_error("degenerate window"); delete q; return OG_E_INVAL; }
     uint64_t nb = d->interval ? (uint64_t)(e1 - s0) / (uint64_t)p.interval : 1;

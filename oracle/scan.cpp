@@ -179,8 +179,10 @@ void interval_to_record(const IntervalRecord &ir, Record &rec) {
 
 } // namespace
 
-int scan_aggregate(const og_shard_desc &sh, const og_query_desc &q, int threads, uint32_t series_begin,
+int scan_aggregate(const og_shard_desc &sh, const og_query_desc &q_in, int threads, uint32_t series_begin,
                    uint32_t series_end, ScanResult &out) {
+    og_query_desc q = q_in; /* influxql.MinTime/MaxTime (ast.go:92,102) bound the range */
+    q.tmin = std::max(q_in.tmin, (int64_t)(INT64_MIN + 2)); q.tmax = std::min(q_in.tmax, (int64_t)(INT64_MAX - 1));
     if (!q.ascending) return E_UNSUPPORTED;
     if (series_end > sh.n_series) series_end = sh.n_series;
     /* schemas: the input record holds every column a call or the filter touches (+ time) */
@@ -205,10 +207,15 @@ int scan_aggregate(const og_shard_desc &sh, const og_query_desc &q, int threads,
 
     WindowOpt w; w.interval = q.interval; w.offset = q.offset; w.start_time = q.tmin; w.end_time = q.tmax;
     /* TimeWindowsInit agg_tagset_cursor.go:1012-1027 with FileInfo.{Min,Max}Time = query range (updateQueryTime :448-463) */
+    /* the file range is intersected with the query range before it reaches TimeWindowsInit (fileLoopCursor.updateQueryTime) */
+    int64_t sh_min = INT64_MAX, sh_max = INT64_MIN;
+    for (uint32_t g = 0; g < sh.n_segments; g++) { sh_min = std::min(sh_min, sh.seg_tmin[g]); sh_max = std::max(sh_max, sh.seg_tmax[g]); }
+    int64_t gmin = std::max(q.tmin, sh_min), gmax = std::min(q.tmax, sh_max);
+    if (gmin > gmax) gmin = gmax = q.tmin; /* no overlap: one empty window */
     int64_t min_s, min_e, max_s, max_e;
-    window(w, q.tmin, &min_s, &min_e);
+    if (q.interval == 0) { min_s = gmin; min_e = gmax + 1; max_s = min_s; max_e = min_e; }
+    else { window(w, gmin, &min_s, &min_e); window(w, gmax + 1, &max_s, &max_e); }
     int64_t interval_time = min_e - min_s;
-    window(w, q.tmax + 1, &max_s, &max_e);
     bool has_interval = q.interval != 0;
 
     uint32_t n_groups = q.group_mode == OG_GROUP_ALL ? 1 : q.group_mode == OG_GROUP_PER_SERIES ? sh.n_series : q.n_groups;
