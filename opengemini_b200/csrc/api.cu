@@ -133,6 +133,7 @@ OG_API void og_shard_close(og_shard *s) {
     cudaFree(s->d_page_off); cudaFree(s->d_page_len); cudaFree(s->d_sids);
     if (s->h_seg_buf) cudaFreeHost(s->h_seg_buf);
     if (s->d_seg_buf) cudaFree(s->d_seg_buf);
+    for (auto &c : s->il) { cudaFree(c.words); cudaFree(c.grp_off); cudaFree(c.grp_words); cudaFree(c.ok); }
     delete s;
 }
 
@@ -352,6 +353,7 @@ struct Plan { /* built once per query, reused by every og_query_run */
     bool fused;
     uint8_t *cls;   /* per-segment class (SEG_FAST / SEG_GENERAL) when the fast Gorilla kernel applies, else nullptr */
     int fm; bool times;
+    IlP il;
 };
 template <class T> int salloc(og_query *q, T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) q->scratch.push_back(*p); return rc; }
 
@@ -359,14 +361,16 @@ template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP
     uint32_t n = ch.seg_end - ch.seg_begin;
     k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch, cls);
 }
-template <int FM, bool TIMES> void launch_fast_t(int stage, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
-    uint32_t n = ch.seg_end - ch.seg_begin;
-    dim3 grid((n + OG_FAST_THREADS - 1) / OG_FAST_THREADS), block(OG_FAST_THREADS);
-    (void)stage;
-    k_fused_fast<FM, TIMES><<<grid, block, 0, st>>>(d, p, ch, cls);
+struct FastArgs { IlP il; };
+template <int FM, bool TIMES> void launch_fast_t(const FastArgs &fa, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
+    /* lane groups are absolute (segment / 32); a group that straddles the chunk boundary runs with the lanes of this chunk */
+    uint32_t g0 = ch.seg_begin / 32, g1 = (ch.seg_end + 31) / 32;
+    constexpr uint32_t WPB = OG_FAST_THREADS / 32;
+    dim3 grid((g1 - g0 + WPB - 1) / WPB), block(OG_FAST_THREADS);
+    k_fused_fast<FM, TIMES><<<grid, block, 0, st>>>(d, p, ch, cls, fa.il, g0);
 }
 /* a handful of aggregate-set specialisations; anything else runs the all-aggregates instance */
-void launch_fast(int fm, bool times, int stage, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
+void launch_fast(int fm, bool times, const FastArgs &stage, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
     if (!times) {
         switch (fm) {
         case FM_SUM | FM_COUNT: return launch_fast_t<FM_SUM | FM_COUNT, false>(stage, d, p, ch, cls, st);
@@ -383,6 +387,47 @@ void launch_fast(int fm, bool times, int stage, const DirP &d, const QueryP &p, 
         }
     }
     return launch_fast_t<63, true>(stage, d, p, ch, cls, st);
+}
+
+/* Build (once per shard and column) the lane-interleaved stream copy that k_fused_fast reads.  Returns OG_OK with
+ * state 1 (ready) or -1 (nothing eligible / not enough memory: the general fused kernel serves the column instead). */
+int ensure_il(og_shard *s, int col, cudaStream_t st) {
+    if (s->il.size() != s->n_columns) s->il.resize(s->n_columns);
+    og_shard::IlCol &ic = s->il[col];
+    if (ic.state != 0) return OG_OK;
+    ic.state = -1;
+    if (s->n_segments == 0 || s->col_types[col] != OG_TYPE_FLOAT) return OG_OK;
+    const uint32_t ng = (s->n_segments + 31) / 32;
+    uint32_t *seg_words = nullptr;
+    int rc;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    if ((rc = dalloc(&ic.ok, (size_t)s->n_segments))) return rc;
+    if ((rc = dalloc(&seg_words, (size_t)s->n_segments))) return rc;
+    if ((rc = dalloc(&ic.grp_words, (size_t)ng))) { cudaFree(seg_words); return rc; }
+    if ((rc = dalloc(&ic.grp_off, (size_t)ng))) { cudaFree(seg_words); return rc; }
+    DirP d = make_dir(s);
+    k_il_scan<<<(s->n_segments + 255) / 256, 256, 0, st>>>(d, col, s->col_types[col], ic.ok, seg_words);
+    k_il_group_words<<<(ng * 32 + 255) / 256, 256, 0, st>>>(s->n_segments, seg_words, ic.grp_words);
+    std::vector<uint32_t> gw(ng); std::vector<uint64_t> go(ng);
+    CU(cudaMemcpyAsync(gw.data(), ic.grp_words, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(seg_words);
+    uint64_t total = 0;
+    for (uint32_t g = 0; g < ng; g++) { go[g] = total; total += (uint64_t)gw[g] * 32; }
+    if (total == 0) return OG_OK;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (total * 4 + ((size_t)8 << 30) > free_b) return OG_OK; /* keep headroom for the query scratch: fall back to the general kernel */
+    if (cudaMalloc(&ic.words, total * 4) != cudaSuccess) { cudaGetLastError(); ic.words = nullptr; return OG_OK; }
+    CU(cudaMemcpyAsync(ic.grp_off, go.data(), (size_t)ng * 8, cudaMemcpyHostToDevice, st));
+    k_il_repack<<<(ng * 32 + 127) / 128, 128, 0, st>>>(d, col, ic.ok, ic.grp_off, ic.grp_words, ng, ic.words);
+    CU(cudaGetLastError());
+    cudaEventRecord(e1, st);
+    CU(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ic.n_words = total; ic.build_ms = ms; ic.state = 1;
+    return OG_OK;
 }
 
 int build_plan(og_query *q) {
@@ -451,8 +496,13 @@ int build_plan(og_query *q) {
     q->path_used = pl->fused ? 1 : 0;
     if (pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments) {
         /* classify once: which segments the specialised Gorilla kernel takes (the rest go to k_fused_segment) */
+        if ((rc = ensure_il(s, p.col_index[0], st))) return rc;
+    }
+    if (pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments && s->il[p.col_index[0]].state == 1) {
+        const og_shard::IlCol &ic = s->il[p.col_index[0]];
+        pl->il.words = ic.words; pl->il.grp_off = ic.grp_off; pl->il.grp_words = ic.grp_words; pl->il.ok = ic.ok;
         if ((rc = salloc(q, &pl->cls, (size_t)s->n_segments))) return rc;
-        k_classify<<<(s->n_segments + 255) / 256, 256, 0, st>>>(make_dir(s), p, pl->cls);
+        k_classify<<<(s->n_segments + 255) / 256, 256, 0, st>>>(make_dir(s), p, ic.ok, pl->cls);
         CU(cudaGetLastError());
         pl->fm = 0; pl->times = false;
         for (uint32_t c = 0; c < p.n_calls; c++) {
@@ -513,7 +563,7 @@ OG_API int og_query_run(og_query *q) {
         for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)(b - a) * p.n_buckets, st));
         CU(cudaEventRecord(q->main_ev[2 * chunks_run], st));
         if (pl->fused) {
-            if (pl->cls) { launch_fast(pl->fm, pl->times, 0, dir, p, ch, pl->cls, st); launches++; }
+            if (pl->cls) { launch_fast(pl->fm, pl->times, FastArgs{pl->il}, dir, p, ch, pl->cls, st); launches++; }
             switch (p.n_calls) {
             case 1: launch_fused<1>(dir, p, ch, pl->cls, st); break;
             case 2: launch_fused<2>(dir, p, ch, pl->cls, st); break;

@@ -1,26 +1,28 @@
 /*
  * fused_fast.cuh — K5 specialised for the headline shape: float64 Gorilla pages (tag 3, no nulls) with const-delta
- * time pages.  One thread per segment (a warp = 32 consecutive segments), built for instruction count and for the
- * memory system:
+ * time pages.  One thread per segment, a warp = 32 consecutive segments ("lane group").
  *
- *   staging   each lane owns a 256-byte ring (4 slots x 64 B, + 8 mirror bytes) in shared memory that holds the next
- *             bytes of ITS page.  The warp refills rings cooperatively: whenever some lanes ("owners") have a free
- *             slot, every group of 8 lanes copies one owner's next 64-byte chunk with one 8-byte cp.async each
- *             (LDGSTS: fully coalesced 64 B segments, no register staging, asynchronous), and signals that owner's
- *             per-slot mbarrier (cp.async.mbarrier.arrive).  Owners wait on their own mbarrier just before they enter
- *             a chunk — two chunks after it was requested — so DRAM latency is off the critical path.
- *             The 264-byte ring stride skews lanes by 8 bytes: LDS from lanes that run in lockstep are 2-way at worst.
- *   decode    stateless bit addressing: the 64 bits at bit position p come from three LDS.32 + three PRMT (byte swap)
- *             + two funnel shifts (the mirror bytes make the three words never wrap); the '10' (window reuse) record —
+ *   layout    Gorilla decode is serial per stream, so a warp reads 32 different pages.  To make those reads coalesced
+ *             the shard keeps, next to the pages, a LANE-INTERLEAVED copy of every eligible stream (built once per
+ *             shard and column by k_il_repack, on first use): the streams of a lane group are cut into 32-bit
+ *             big-endian words and word w of lane l is stored at  il[grp_off + w*32 + l].  One 128-byte row therefore
+ *             holds word w of all 32 lanes: a warp-wide 4-byte access is one fully used line, in HBM and in shared
+ *             memory alike, whatever the lanes' individual positions are.
+ *   staging   each lane copies ITS words with 4-byte cp.async (LDGSTS) into the warp's shared-memory window
+ *             [64 rows + 2 mirror rows][32 lanes]; bank = lane, so neither the copies nor the loads ever conflict.
+ *             cp.async groups are per thread: no mbarrier, no cross-lane signalling, no uniform-datapath waterfall.
+ *             Refill runs on a fixed schedule (every K records): a record consumes <= 77 bits, so a 64-word window
+ *             refilled every 8 records always holds two service periods of look-ahead (see the proof at the loop).
+ *   decode    stateless bit addressing: the 64 bits at bit position p are three LDS.32 at immediate row offsets + two
+ *             funnel shifts (words are pre-swapped to native order by the repack); the '10' (window reuse) record —
  *             >95% of records on noisy-mantissa data — is then one shift + mask + xor and p += 2+m.
  *   reduce    window boundaries are row countdowns derived from the const-delta time page (no time decode and no
  *             division in the loop); partials stay in registers and are flushed to the same edge/cell arrays the
  *             general kernel uses, so k_fix_edges / k_merge_groups are shared and float sums keep the reference's
  *             left-to-right order.
  *
- * A TMA variant of the staging (per-lane cp.async.bulk, UBLKCP) was measured first: the uniform-datapath waterfall
- * (9 warp instructions per 128-byte copy) plus divergent per-lane service made it 3x more instructions per value;
- * see profiles/r01_fast_kernel_history.md.
+ * Earlier staging designs (per-lane TMA bulk copies, warp-cooperative cp.async + mbarriers) read the pages where they
+ * lie; both spent more instructions on staging than on decoding — see profiles/r01_fast_kernel_history.md.
  *
  * Replaces for eligible segments: tsm1.FloatArrayDecodeAll (batch_float.go:278-514) + Time.constDeltaDecoding
  * (timestamp.go:190) + FilterByTime (reader.go:754) + getIntervalIndex/reduce (aggregate_cursor.go:306-356) +
@@ -35,74 +37,118 @@ namespace ogpu {
 /* ---- PTX wrappers ---- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("mov.u32 %0, %0;" : "+r"(x)); return x; } /* keeps a value in a register instead of being rematerialised */
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-/* 8-byte asynchronous global->shared copy (LDGSTS) and its completion hook on an mbarrier */
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
+/* 4-byte asynchronous global->shared copy (LDGSTS.32); groups are per thread */
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <int OFF> __device__ __forceinline__ uint32_t lds32o(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
-__device__ __forceinline__ uint64_t lds64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
 
 enum { FM_COUNT = 1, FM_SUM = 2, FM_MIN = 4, FM_MAX = 8, FM_FIRST = 16, FM_LAST = 32 };
 enum { SEG_GENERAL = 0, SEG_FAST = 1 };  /* per-segment classes computed by k_classify */
 
 #define OG_FAST_THREADS 128
-#define OG_FAST_CH 64u         /* bytes per staged chunk */
-#define OG_FAST_NS 4u          /* ring slots per lane */
-#define OG_FAST_RING 256u      /* ring bytes per lane */
-#define OG_FAST_STRIDE 264u    /* ring + 8 mirror bytes; 8-byte skew between lanes */
+#define OG_IL_NW 64u            /* window rows (words per lane) */
+#define OG_IL_ROWS 66u          /* + 2 mirror rows: rows 64,65 repeat rows 0,1 so that three consecutive rows never wrap */
+#define OG_IL_PAD_WORDS 6u      /* words appended to every stream: the decoder may touch 77 + 64 bits past the last record */
+#define OG_IL_HDR 7u            /* page = [31][rows u32][0x30][0x10] | stream: first value 8 B BE, records... */
 
-/* per-segment eligibility for the fast kernel (one thread per segment, header bytes only; run once per query plan) */
-__global__ void k_classify(DirP d, QueryP q, uint8_t *cls) {
+/* lane-interleaved stream copy of one column (owned by the shard, built lazily) */
+struct IlP {
+    const uint32_t *words;     /* il[grp_off[g] + w*32 + lane] */
+    const uint64_t *grp_off;   /* [n_groups32] in words */
+    const uint32_t *grp_words; /* [n_groups32] words per lane in this group (0: no eligible lane) */
+    const uint8_t *ok;         /* [n_segments] static eligibility (codec + header shape) */
+};
+
+/* static eligibility + stream length in words (one thread per segment; header bytes only) */
+__global__ void k_il_scan(DirP d, int col, int col_type, uint8_t *ok, uint32_t *seg_words) {
     uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= d.n_segments) return;
-    uint8_t c = SEG_GENERAL;
+    uint8_t c = 0; uint32_t nw = 0;
     uint32_t rows = d.seg_rows[seg];
-    if (!(d.seg_tmax[seg] < q.tmin || d.seg_tmin[seg] > q.tmax || rows < 2) && q.col_type[0] == OG_TYPE_FLOAT) {
-        size_t pi = (size_t)q.col_index[0] * d.n_segments + seg, ti = (size_t)d.n_columns * d.n_segments + seg;
+    if (rows >= 2 && col_type == OG_TYPE_FLOAT) {
+        size_t pi = (size_t)col * d.n_segments + seg, ti = (size_t)d.n_columns * d.n_segments + seg;
         const uint8_t *p = d.data + d.page_off[pi], *t = d.data + d.page_off[ti];
         uint32_t len = d.page_len[pi], tlen = d.page_len[ti];
         /* value page: [31][u32 rows][0x30][0x10][8 B first]...; time page: [32][u32 rows][0x10][t0][uvarint dt][uvarint n-1] */
         if (len >= 16 && tlen >= 16 && __ldg(p) == 31 && (__ldg(p + 5) >> 4) == 3 && __ldg(t) == 32 && (__ldg(t + 5) >> 4) == 1) {
             TimeDesc td;
-            if (parse_time_page(t, tlen, td) == D_OK && td.kind == 0 && td.delta > 0 && td.delta < (1ull << 40) && ld_be32(p + 1) == rows) c = SEG_FAST;
+            if (parse_time_page(t, tlen, td) == D_OK && td.kind == 0 && td.delta > 0 && td.delta < (1ull << 40) && ld_be32(p + 1) == rows) {
+                c = 1; nw = (len - OG_IL_HDR + 3) / 4 + OG_IL_PAD_WORDS;
+            }
         }
     }
-    cls[seg] = c;
+    ok[seg] = c; seg_words[seg] = nw;
 }
 
-/* 64 bits of the stream at bit position p, from the lane's ring (ring + mirror: the three words never wrap) */
-__device__ __forceinline__ uint64_t fetch64(uint32_t ring, uint32_t p) {
-    uint32_t a = ring + ((p >> 3) & (OG_FAST_RING - 4));
-    uint32_t a0 = lds32o<0>(a), a1 = lds32o<4>(a), a2 = lds32o<8>(a);
-    a0 = __byte_perm(a0, 0, 0x0123); a1 = __byte_perm(a1, 0, 0x0123); a2 = __byte_perm(a2, 0, 0x0123);
+/* words per lane of every lane group = max over its eligible lanes (one warp per group) */
+__global__ void k_il_group_words(uint32_t n_segments, const uint32_t *seg_words, uint32_t *grp_words) {
+    uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    uint32_t seg = g * 32 + lane;
+    uint32_t w = seg < n_segments ? seg_words[seg] : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (lane == 0 && g * 32 < n_segments) grp_words[g] = w;
+}
+
+/* the repack: word w of lane l -> il[grp_off + w*32 + l], big-endian stream words stored in native order (one warp per group) */
+__global__ void k_il_repack(DirP d, int col, const uint8_t *ok, const uint64_t *grp_off, const uint32_t *grp_words, uint32_t n_groups,
+                            uint32_t *il) {
+    uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n_groups) return;
+    uint32_t nw = grp_words[g];
+    if (nw == 0) return;
+    uint32_t seg = g * 32 + lane;
+    bool live = seg < d.n_segments && ok[seg];
+    const uint32_t *base = nullptr; uint32_t sh = 0, own_words = 0;
+    if (live) {
+        size_t pi = (size_t)col * d.n_segments + seg;
+        const uint8_t *s = d.data + d.page_off[pi] + OG_IL_HDR;
+        base = (const uint32_t *)((uintptr_t)s & ~(uintptr_t)3);
+        sh = (uint32_t)((uintptr_t)s & 3);
+        own_words = (d.page_len[pi] - OG_IL_HDR + 3) / 4 + OG_IL_PAD_WORDS; /* bytes past the page are the next page or the shard's tail padding */
+    }
+    uint32_t *out = il + grp_off[g] + lane;
+    /* bytes s[4w..4w+3] big-endian: from aligned words a=base[w], b=base[w+1] (little-endian loads) */
+    const uint32_t sel = sh == 0 ? 0x0123u : sh == 1 ? 0x1234u : sh == 2 ? 0x2345u : 0x3456u;
+    uint32_t a = live ? __ldg(base) : 0;
+    for (uint32_t w = 0; w < nw; w++) {
+        uint32_t v = 0;
+        if (w < own_words) {
+            uint32_t b = __ldg(base + w + 1);
+            v = __byte_perm(a, b, sel);
+            a = b;
+        }
+        out[(size_t)w * 32] = v;
+    }
+}
+
+/* per-query classes: eligible by codec (IlP.ok) and overlapping the query's time range */
+__global__ void k_classify(DirP d, QueryP q, const uint8_t *ok, uint8_t *cls) {
+    uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= d.n_segments) return;
+    cls[seg] = (ok[seg] && !(d.seg_tmax[seg] < q.tmin || d.seg_tmin[seg] > q.tmax)) ? SEG_FAST : SEG_GENERAL;
+}
+
+/* 64 bits of the stream at bit position p: rows (p>>5), +1, +2 of the lane's window column */
+__device__ __forceinline__ uint64_t fetch64(uint32_t col, uint32_t p) {
+    uint32_t a = col + ((p << 2) & ((OG_IL_NW - 1) << 7)); /* ((p >> 5) % NW) * 128 */
+    uint32_t a0 = lds32o<0>(a), a1 = lds32o<128>(a), a2 = lds32o<256>(a);
     uint32_t hi = __funnelshift_l(a1, a0, p), lo = __funnelshift_l(a2, a1, p); /* shift amount taken mod 32 */
     return ((uint64_t)hi << 32) | lo;
 }
 
 template <int FM, bool TIMES>
-__global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q, ChunkP ch, const uint8_t *cls) {
-    constexpr uint32_t CH = OG_FAST_CH, NS = OG_FAST_NS, STRIDE = OG_FAST_STRIDE;
-    constexpr uint32_t AHEAD = 24; /* bytes past the read position that a record decode may touch (13 + 64 bits, word-granular loads) */
+__global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q, ChunkP ch, const uint8_t *cls, IlP il, uint32_t grp_begin) {
+    constexpr uint32_t NW = OG_IL_NW;
     constexpr uint32_t FULL = 0xffffffffu;
-    __shared__ __align__(128) uint8_t s_ring[OG_FAST_THREADS * STRIDE];
-    __shared__ __align__(8) uint64_t s_bar[OG_FAST_THREADS * NS];
-    __shared__ __align__(8) uint64_t s_src[OG_FAST_THREADS]; /* 8-byte aligned stream base of every lane */
+    __shared__ __align__(128) uint32_t s_win[(OG_FAST_THREADS / 32) * OG_IL_ROWS * 32];
 
-    const uint32_t lane = threadIdx.x & 31, wbase = threadIdx.x & ~31u;
-    const uint32_t seg = ch.seg_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = seg < ch.seg_end && cls[seg < ch.seg_end ? seg : ch.seg_begin] == SEG_FAST;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t grp = grp_begin + blockIdx.x * (OG_FAST_THREADS / 32) + wid;
+    const uint32_t seg = grp * 32 + lane;
+    /* a lane group that straddles two chunks runs in both, with complementary lanes */
+    bool active = seg >= ch.seg_begin && seg < ch.seg_end && cls[seg] == SEG_FAST;
     if (!__any_sync(FULL, active)) return;
     const size_t e = 2 * (size_t)(seg - ch.seg_begin);
 
@@ -123,59 +169,21 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
         if (r_lo > r_hi || r_lo >= rows) { ch.edge_bucket[e] = OG_NO_BUCKET; ch.edge_bucket[e + 1] = OG_NO_BUCKET; active = false; }
     }
 
-    /* ---- stream: page = [31][rows u32][0x30][0x10] | first value 8 B BE | records... ---- */
-    uint32_t skip = 0, n_chunks = 0;
-    {
-        const uint8_t *g8 = d.data;
-        if (active) {
-            const size_t pi = (size_t)q.col_index[0] * d.n_segments + seg;
-            const uint8_t *stream = d.data + d.page_off[pi] + 7;
-            const uint32_t stream_len = d.page_len[pi] - 7;
-            g8 = (const uint8_t *)((uintptr_t)stream & ~(uintptr_t)7);
-            skip = (uint32_t)(stream - g8);
-            n_chunks = (skip + stream_len + AHEAD + CH - 1) / CH;
-        }
-        s_src[threadIdx.x] = (uint64_t)(uintptr_t)g8;
-    }
-    const uint32_t ring = opaque(smem_u32(s_ring) + threadIdx.x * STRIDE);
-    const uint32_t bar0 = opaque(smem_u32(s_bar) + threadIdx.x * NS * 8);
-    /* every chunk is written by 8 cp.async (one per serving lane) + the owner's own arrival (mirror copy or plain) */
-#pragma unroll
-    for (uint32_t i = 0; i < NS; i++) mbar_init(bar0 + 8 * i, 9);
-    __syncwarp();
-
-    /* serving side, fixed mapping: in step j this lane copies piece (lane&7) of the chunk of owner 4j + (lane>>3) */
-    const uint32_t sv_dst0 = opaque(smem_u32(s_ring) + (wbase + (lane >> 3)) * STRIDE + 8 * (lane & 7));
-    const uint32_t sv_bar0 = opaque(smem_u32(s_bar) + (wbase + (lane >> 3)) * NS * 8);
-    const uint32_t sv_src0 = opaque(smem_u32(s_src) + (wbase + (lane >> 3)) * 8);
-    const uint32_t my_src = opaque(smem_u32(s_src) + threadIdx.x * 8);
-    uint32_t staged = 0; /* chunks requested so far by this lane */
-    /* one cooperative round: every lane with want!=0 gets chunk `staged` copied into slot staged%NS */
-    auto coop_round = [&](bool want) {
-        const uint32_t req = want ? staged : FULL;
-        const uint32_t wm = __ballot_sync(FULL, want);
-#pragma unroll
-        for (uint32_t j = 0; j < 8; j++) {
-            if (((wm >> (4 * j)) & 0xfu) == 0) continue; /* warp-uniform */
-            uint32_t c = __shfl_sync(FULL, req, 4 * j + (lane >> 3));
-            if (c != FULL) {
-                uint64_t base = lds64(sv_src0 + 32 * j);
-                uint32_t sl = c % NS;
-                cp_async8(sv_dst0 + j * (4 * STRIDE) + sl * CH, (const uint8_t *)(uintptr_t)base + (size_t)c * CH + 8 * (lane & 7));
-                cp_async_arrive(sv_bar0 + j * (4 * NS * 8) + sl * 8);
-            }
-        }
-        if (want) {
-            uint32_t sl = staged % NS;
-            if (sl == 0) { /* mirror: the first 8 bytes of slot 0 again after the ring end */
-                cp_async8(ring + OG_FAST_RING, (const uint8_t *)(uintptr_t)lds64(my_src) + (size_t)staged * CH);
-                cp_async_arrive(bar0);
-            } else mbar_arrive(bar0 + 8 * sl);
-            staged++;
+    /* ---- the lane's column of the warp window, and its interleaved source ---- */
+    const uint32_t col = opaque(smem_u32(s_win) + wid * (OG_IL_ROWS * 128) + lane * 4);
+    const uint32_t n_words = active ? il.grp_words[grp] : 0;
+    const uint32_t *src = il.words + (active ? il.grp_off[grp] : 0) + lane; /* word `issued` is at src[0] */
+    uint32_t issued = 0;
+    auto refill = [&](uint32_t lim) { /* copy words [issued, lim) */
+        while (issued < lim) {
+            uint32_t r = issued & (NW - 1);
+            cp_async4(col + r * 128, src);
+            if (r < 2) cp_async4(col + (NW + r) * 128, src);
+            src += 32; issued++;
         }
     };
-#pragma unroll
-    for (uint32_t i = 0; i < NS; i++) coop_round(active && staged < n_chunks);
+    refill(min(NW, n_words));
+    cp_async_commit();
 
     /* ---- window bookkeeping: bucket of row r_lo, first row of the next bucket (rb), Bresenham advance of rb ---- */
     uint32_t cur_b = 0, rb = 0xffffffffu, step_q = 0; uint64_t rem = 0, step_r = 0;
@@ -225,25 +233,13 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
     };
 
     /* ---- decode state ---- */
-    uint32_t p = skip * 8;   /* bit position of the next unread bit (relative to the 8-byte aligned stream base) */
-    uint32_t landed = 0;     /* chunks [0, landed) have been waited for */
+    uint32_t p = 0;          /* bit position of the next unread bit of the lane's stream */
     uint32_t m = 64, tr = 0, sr = 0, kfast = 0; uint64_t MASK = 0; bool fastok = false, bad = false;
     bool done = !active;
-    /* Service runs on a fixed schedule — every K iterations, for the whole warp — because per-lane triggers would fire
-     * in almost every iteration (32 unsynchronised lanes, one event per ~10 records each).  A record consumes at most
-     * 77 bits, so between two services a lane touches at most [b, b + 10*K + AHEAD): that much must have landed. */
-    constexpr uint32_t K = 8, SPAN = 10 * K + AHEAD;
-    auto lane_wait_ahead = [&]() {
-        uint32_t b = p >> 3;
-        if (b > skip + (n_chunks * CH)) { bad = true; done = true; return; } /* ran past the page: corrupt stream */
-        uint32_t target = (b + SPAN + CH - 1) / CH;
-        if (target > staged) target = staged;
-        while (landed < target) { mbar_wait(bar0 + 8 * (landed % NS), (landed / NS) & 1); landed++; }
-    };
-    auto want_now = [&]() -> bool { return !done && staged < n_chunks && (p >> 3) >= (staged + 1 - NS) * CH; };
 
+    cp_async_wait<0>();
     uint64_t val = 0;
-    if (active) { lane_wait_ahead(); val = fetch64(ring, p); p += 64; } /* first value: 64 raw bits */
+    if (active) { val = fetch64(col, 0); p = 64; } /* first value: 64 raw bits */
 
     /* ---- row events: skip rows before r_lo, window boundaries, end at r_hi ---- */
     bool skipping = r_lo > 0;
@@ -251,16 +247,17 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
     uint32_t n_ev = stop; /* rows until the next event (row 0 is current) */
     if (!skipping) { mn = mx = fi = val; n_mn = n_mx = n_ev; }
 
+    /* Refill schedule.  Service s (every K records) copies words up to (p_s>>5) + NW and then waits for the PREVIOUS
+     * service's group, i.e. for words < (p_{s-1}>>5) + NW.  Until service s+1 the lane reads at most 77 + 64 bits past
+     * p_{s+1} <= p_{s-1} + 2*K*77, i.e. words <= (p_{s-1}>>5) + (2*8*77 + 141)/32 + 3 = (p_{s-1}>>5) + 46 < NW. */
+    constexpr uint32_t K = 8;
     for (uint32_t it = 0;; it++) {
-        /* ---- warp service: staging rounds + landing waits (warp-uniform schedule) ---- */
         if ((it & (K - 1)) == 0) {
-            for (;;) {
-                bool w = want_now();
-                if (!__any_sync(FULL, w)) break;
-                coop_round(w);
-            }
-            if (!done) lane_wait_ahead();
             if (__all_sync(FULL, done)) break;
+            if (!done && (p >> 5) > n_words) { bad = true; done = true; } /* ran past the stream: corrupt page */
+            if (!done) refill(min((p >> 5) + NW, n_words));
+            cp_async_commit();
+            cp_async_wait<1>();
         }
         if (done) continue;
         if (n_ev == 0) { /* current row == stop */
@@ -287,8 +284,8 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
         if (FM & FM_MAX) { if (u2d(mx) < u2d(val)) { mx = val; if (TIMES) n_mx = n_ev; } }
         if (FM & FM_LAST) lastv = val;
         n_ev--;
-        /* next record (batch_float.go:352-508); service guarantees AHEAD readable bytes at p */
-        uint64_t x = fetch64(ring, p);
+        /* next record (batch_float.go:352-508) */
+        uint64_t x = fetch64(col, p);
         uint32_t ctrl = (uint32_t)(x >> 62);
         if (ctrl == 2 && fastok) { /* '10': reuse the window */
             val ^= (x >> sr) & MASK;
@@ -305,7 +302,7 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
                 sr = lead - 2; kfast = 2 + m;
                 MASK = (m == 64 ? ~0ull : ((1ull << m) - 1)) << tr;
             } else p += 2;
-            uint64_t y = fetch64(ring, p);
+            uint64_t y = fetch64(col, p);
             uint64_t sig = m == 64 ? y : (y >> (64 - m));
             p += m;
             val ^= sig << tr;
@@ -317,7 +314,7 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
         ch.edge_bucket[e + 1] = (head_b == OG_NO_BUCKET || cur_b == head_b) ? OG_NO_BUCKET : cur_b;
     }
     /* copies still in flight must land before this CTA's shared memory can be reused */
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    cp_async_wait<0>();
 }
 
 } // namespace ogpu

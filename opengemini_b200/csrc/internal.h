@@ -49,6 +49,11 @@ struct og_shard {
     void *h_seg_buf = nullptr; size_t h_seg_buf_bytes = 0;
     void *d_seg_buf = nullptr; size_t d_seg_buf_bytes = 0;
     std::vector<og_colval_view> seg_views;
+    /* lane-interleaved stream copy per column for the fast Gorilla kernel (fused_fast.cuh), built on first use */
+    struct IlCol { int state = 0; /* 0 not built, 1 ready, -1 unavailable (no eligible segment / out of memory) */
+                   uint32_t *words = nullptr; uint64_t *grp_off = nullptr; uint32_t *grp_words = nullptr; uint8_t *ok = nullptr;
+                   uint64_t n_words = 0; double build_ms = 0; };
+    std::vector<IlCol> il; /* [n_columns] */
 };
 
 namespace ogpu {
