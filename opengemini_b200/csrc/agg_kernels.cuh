@@ -305,14 +305,15 @@ __global__ void k_merge_groups(QueryP q, ChunkP ch, GroupP gp) {
         lo = a;
     }
     if (lo >= hi || gp.grp_series[lo] >= ch.series_end) return;
-    for (uint32_t c = 0; c < q.n_calls; c++) {
+    { /* one thread per (group, bucket, call): blockIdx.y = call */
+        const uint32_t c = blockIdx.y;
         const CallP &cp = q.calls[c];
         Part acc = load_part(gp.dense[c], idx);
         const Tri cells = ch.cells[c];
         /* The fold is strictly sequential in series order (that is the reference's order, reccord_functions.go:730-733),
          * but the loads do not depend on it: fetch a batch of U partials first, so each thread keeps U independent
          * loads in flight (16,667 bucket threads alone cannot hide DRAM latency). */
-        constexpr int U = 8;
+        constexpr int U = 16;
         for (uint32_t i = lo; i < hi; i += U) {
             uint32_t okv[U]; uint64_t vv[U]; int64_t tt[U];
 #pragma unroll

@@ -247,8 +247,12 @@ static void window_of(int64_t interval, int64_t offset, int64_t tmin, int64_t tm
     *s = st; *e = en;
 }
 
+} /* extern "C" */
+namespace { void free_plan(void *plan); }
+extern "C" {
 OG_API void og_query_destroy(og_query *q) {
     if (!q) return;
+    free_plan(q->plan);
     for (void *p : q->scratch) cudaFree(p);
     for (int c = 0; c < OG_MAX_CALLS; c++) { cudaFree(q->dense[c].val); cudaFree(q->dense[c].ok); cudaFree(q->dense[c].tim); }
     cudaFree(q->d_group_of_series);
@@ -354,12 +358,14 @@ struct Plan { /* built once per query, reused by every og_query_run */
     uint8_t *cls;   /* per-segment class (SEG_FAST / SEG_GENERAL) when the fast Gorilla kernel applies, else nullptr */
     int fm; bool times;
     IlP il;
+    uint32_t *cls_list[2];              /* device: sorted ids of the SEG_GENERAL [0] / SEG_RAW [1] segments (k_fused_segment / k_fused_raw) */
+    std::vector<uint32_t> *cls_host[2]; /* same, on the host (per-chunk ranges are found by binary search) */
 };
+void free_plan(void *plan) { Plan *pl = (Plan *)plan; if (pl) { delete pl->cls_host[0]; delete pl->cls_host[1]; delete pl; } }
 template <class T> int salloc(og_query *q, T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) q->scratch.push_back(*p); return rc; }
 
-template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
-    uint32_t n = ch.seg_end - ch.seg_begin;
-    k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch, cls);
+template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP &ch, const uint32_t *list, uint32_t n, cudaStream_t st) {
+    if (n) k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch, list, n);
 }
 struct FastArgs { IlP il; };
 template <int FM, bool TIMES> void launch_fast_t(const FastArgs &fa, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
@@ -504,6 +510,24 @@ int build_plan(og_query *q) {
         if ((rc = salloc(q, &pl->cls, (size_t)s->n_segments))) return rc;
         k_classify<<<(s->n_segments + 255) / 256, 256, 0, st>>>(make_dir(s), p, ic.ok, pl->cls);
         CU(cudaGetLastError());
+        /* compact the segments the Gorilla kernel does not take, per class, so that their kernels run with full warps */
+        uint32_t *d_cnt;
+        if ((rc = salloc(q, &d_cnt, 2))) return rc;
+        CU(cudaMemsetAsync(d_cnt, 0, 8, st));
+        for (int k = 0; k < 2; k++) {
+            if ((rc = salloc(q, &pl->cls_list[k], (size_t)s->n_segments))) return rc;
+            k_list_class<<<(s->n_segments + 255) / 256, 256, 0, st>>>(pl->cls, s->n_segments, k == 0 ? (uint8_t)SEG_GENERAL : (uint8_t)SEG_RAW, pl->cls_list[k], d_cnt + k);
+        }
+        uint32_t cnt[2] = {0, 0};
+        CU(cudaMemcpyAsync(cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int k = 0; k < 2; k++) {
+            pl->cls_host[k] = new std::vector<uint32_t>(cnt[k]);
+            if (!cnt[k]) continue;
+            CU(cudaMemcpy(pl->cls_host[k]->data(), pl->cls_list[k], (size_t)cnt[k] * 4, cudaMemcpyDeviceToHost));
+            std::sort(pl->cls_host[k]->begin(), pl->cls_host[k]->end());
+            CU(cudaMemcpy(pl->cls_list[k], pl->cls_host[k]->data(), (size_t)cnt[k] * 4, cudaMemcpyHostToDevice));
+        }
         pl->fm = 0; pl->times = false;
         for (uint32_t c = 0; c < p.n_calls; c++) {
             pl->fm |= 1 << (p.calls[c].func - 1);
@@ -564,15 +588,27 @@ OG_API int og_query_run(og_query *q) {
         CU(cudaEventRecord(q->main_ev[2 * chunks_run], st));
         if (pl->fused) {
             if (pl->cls) { launch_fast(pl->fm, pl->times, FastArgs{pl->il}, dir, p, ch, pl->cls, st); launches++; }
+            const uint32_t *gl = nullptr; uint32_t gn = nseg;
+            if (pl->cls) { /* leftovers of this chunk: a contiguous range of each sorted list */
+                auto range = [&](int k, const uint32_t **l, uint32_t *cnt) {
+                    auto lo = std::lower_bound(pl->cls_host[k]->begin(), pl->cls_host[k]->end(), ch.seg_begin);
+                    auto hi = std::lower_bound(pl->cls_host[k]->begin(), pl->cls_host[k]->end(), ch.seg_end);
+                    *l = pl->cls_list[k] + (lo - pl->cls_host[k]->begin()); *cnt = (uint32_t)(hi - lo);
+                };
+                range(0, &gl, &gn);
+                const uint32_t *rl; uint32_t rn;
+                range(1, &rl, &rn);
+                if (rn) { k_fused_raw<<<(rn * 32 + 127) / 128, 128, 0, st>>>(dir, p, ch, rl, rn); launches++; }
+            }
             switch (p.n_calls) {
-            case 1: launch_fused<1>(dir, p, ch, pl->cls, st); break;
-            case 2: launch_fused<2>(dir, p, ch, pl->cls, st); break;
-            case 3: launch_fused<3>(dir, p, ch, pl->cls, st); break;
-            case 4: launch_fused<4>(dir, p, ch, pl->cls, st); break;
-            case 5: launch_fused<5>(dir, p, ch, pl->cls, st); break;
-            case 6: launch_fused<6>(dir, p, ch, pl->cls, st); break;
-            case 7: launch_fused<7>(dir, p, ch, pl->cls, st); break;
-            default: launch_fused<8>(dir, p, ch, pl->cls, st); break;
+            case 1: launch_fused<1>(dir, p, ch, gl, gn, st); break;
+            case 2: launch_fused<2>(dir, p, ch, gl, gn, st); break;
+            case 3: launch_fused<3>(dir, p, ch, gl, gn, st); break;
+            case 4: launch_fused<4>(dir, p, ch, gl, gn, st); break;
+            case 5: launch_fused<5>(dir, p, ch, gl, gn, st); break;
+            case 6: launch_fused<6>(dir, p, ch, gl, gn, st); break;
+            case 7: launch_fused<7>(dir, p, ch, gl, gn, st); break;
+            default: launch_fused<8>(dir, p, ch, gl, gn, st); break;
             }
             launches++;
         } else {
@@ -590,7 +626,7 @@ OG_API int og_query_run(og_query *q) {
         CU(cudaEventRecord(q->main_ev[2 * chunks_run + 1], st));
         chunks_run++;
         k_fix_edges<<<(nseg + 127) / 128, 128, 0, st>>>(dir, p, ch);
-        k_merge_groups<<<(unsigned)((cells_dense + 127) / 128), 128, 0, st>>>(p, ch, gp);
+        k_merge_groups<<<dim3((unsigned)((cells_dense + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp);
         launches += 2;
     }
     CU(cudaEventRecord(q->ev1, st));

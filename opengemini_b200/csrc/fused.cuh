@@ -91,10 +91,12 @@ struct FusedState {
 };
 
 template <int NC>
-__global__ void __launch_bounds__(128) k_fused_segment(DirP d, QueryP q, ChunkP ch, const uint8_t *cls) {
-    uint32_t seg = ch.seg_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg >= ch.seg_end) return;
-    if (cls && cls[seg] == 1) return; /* SEG_FAST: handled by k_fused_fast */
+/* `list` (sorted segment ids, `n` of them) selects the segments of this chunk that k_fused_fast did not take, compacted so
+ * that warps stay full; list == nullptr: every segment of the chunk. */
+__global__ void __launch_bounds__(128) k_fused_segment(DirP d, QueryP q, ChunkP ch, const uint32_t *list, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t seg = list ? list[i] : ch.seg_begin + i;
     size_t e = 2 * (size_t)(seg - ch.seg_begin);
     uint32_t rows = d.seg_rows[seg];
     /* segment pruning by directory time range (location.go:276-280) */

@@ -39,12 +39,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("mov.u32 %0, %0;" : "+r"(x)); return x; } /* keeps a value in a register instead of being rematerialised */
 /* 4-byte asynchronous global->shared copy (LDGSTS.32); groups are per thread */
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+template <int DOFF, int SOFF> __device__ __forceinline__ void cp_async4o(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 4;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <int OFF> __device__ __forceinline__ uint32_t lds32o(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
 
 enum { FM_COUNT = 1, FM_SUM = 2, FM_MIN = 4, FM_MAX = 8, FM_FIRST = 16, FM_LAST = 32 };
-enum { SEG_GENERAL = 0, SEG_FAST = 1 };  /* per-segment classes computed by k_classify */
+enum { SEG_GENERAL = 0, SEG_FAST = 1, SEG_RAW = 2 };  /* per-segment classes computed by k_classify */
 
 #define OG_FAST_THREADS 128
 #define OG_IL_NW 64u            /* window rows (words per lane) */
@@ -74,8 +75,12 @@ __global__ void k_il_scan(DirP d, int col, int col_type, uint8_t *ok, uint32_t *
         if (len >= 16 && tlen >= 16 && __ldg(p) == 31 && (__ldg(p + 5) >> 4) == 3 && __ldg(t) == 32 && (__ldg(t + 5) >> 4) == 1) {
             TimeDesc td;
             if (parse_time_page(t, tlen, td) == D_OK && td.kind == 0 && td.delta > 0 && td.delta < (1ull << 40) && ld_be32(p + 1) == rows) {
-                c = 1; nw = (len - OG_IL_HDR + 3) / 4 + OG_IL_PAD_WORDS;
+                c = SEG_FAST; nw = ((len - OG_IL_HDR + 3) / 4 + OG_IL_PAD_WORDS + 7) & ~7u; /* refill copies 8-word batches */
             }
+        } else if (len == 6 + 8 * (size_t)rows && tlen >= 16 && __ldg(p) == 31 && (__ldg(p + 5) >> 4) == 0 && __ldg(t) == 32 && (__ldg(t + 5) >> 4) == 1) {
+            /* raw page (Gorilla output above 90% of raw, float.go:96-99): [31][u32 rows][0x00][rows x 8 B LE] -> k_fused_raw */
+            TimeDesc td;
+            if (parse_time_page(t, tlen, td) == D_OK && td.kind == 0 && td.delta > 0 && td.delta < (1ull << 40) && ld_be32(p + 1) == rows) c = SEG_RAW;
         }
     }
     ok[seg] = c; seg_words[seg] = nw;
@@ -99,7 +104,7 @@ __global__ void k_il_repack(DirP d, int col, const uint8_t *ok, const uint64_t *
     uint32_t nw = grp_words[g];
     if (nw == 0) return;
     uint32_t seg = g * 32 + lane;
-    bool live = seg < d.n_segments && ok[seg];
+    bool live = seg < d.n_segments && ok[seg] == SEG_FAST;
     const uint32_t *base = nullptr; uint32_t sh = 0, own_words = 0;
     if (live) {
         size_t pi = (size_t)col * d.n_segments + seg;
@@ -123,11 +128,74 @@ __global__ void k_il_repack(DirP d, int col, const uint8_t *ok, const uint64_t *
     }
 }
 
-/* per-query classes: eligible by codec (IlP.ok) and overlapping the query's time range */
+/* per-query classes: the static class (IlP.ok) for segments that overlap the query's time range, else SEG_GENERAL */
 __global__ void k_classify(DirP d, QueryP q, const uint8_t *ok, uint8_t *cls) {
     uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= d.n_segments) return;
-    cls[seg] = (ok[seg] && !(d.seg_tmax[seg] < q.tmin || d.seg_tmin[seg] > q.tmax)) ? SEG_FAST : SEG_GENERAL;
+    cls[seg] = (d.seg_tmax[seg] < q.tmin || d.seg_tmin[seg] > q.tmax) ? (uint8_t)SEG_GENERAL : ok[seg];
+}
+
+/* the segments of class `klass`, appended in any order (sorted on the host afterwards) */
+__global__ void k_list_class(const uint8_t *cls, uint32_t n_segments, uint8_t klass, uint32_t *list, uint32_t *count) {
+    uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    bool g = seg < n_segments && cls[seg] == klass;
+    uint32_t m = __ballot_sync(0xffffffffu, g), lane = threadIdx.x & 31;
+    if (m == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (g) list[base + __popc(m & ((1u << lane) - 1))] = seg;
+}
+
+/* Raw float pages with const-delta time: every row is addressable, so one warp takes a segment and each lane reduces one
+ * window (rows of a window sequentially: float sums keep the reference order).  Same outputs as k_fused_segment. */
+__global__ void __launch_bounds__(128) k_fused_raw(DirP d, QueryP q, ChunkP ch, const uint32_t *list, uint32_t n) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint32_t seg = list[i];
+    const size_t e = 2 * (size_t)(seg - ch.seg_begin);
+    const uint32_t rows = d.seg_rows[seg], series = d.seg_series[seg];
+    const size_t ti_idx = (size_t)d.n_columns * d.n_segments + seg;
+    const uint8_t *tp = d.data + d.page_off[ti_idx];
+    const int64_t t0 = (int64_t)ld_be64(tp + 6);
+    uint64_t dtu = 1; ld_uvarint(tp + 14, d.page_len[ti_idx] - 14, &dtu);
+    const int64_t dt = (int64_t)dtu;
+    uint32_t r_lo = 0, r_hi = rows - 1;
+    if (t0 < q.tmin) { uint64_t k = ((uint64_t)(q.tmin - t0) + dtu - 1) / dtu; r_lo = k > rows ? rows : (uint32_t)k; }
+    { int64_t t_last = t0 + (int64_t)(rows - 1) * dt; if (t_last > q.tmax) { if (q.tmax < t0) r_lo = rows; else r_hi = (uint32_t)((uint64_t)(q.tmax - t0) / dtu); } }
+    if (r_lo > r_hi || r_lo >= rows) { if (lane == 0) { ch.edge_bucket[e] = OG_NO_BUCKET; ch.edge_bucket[e + 1] = OG_NO_BUCKET; } return; }
+    const uint8_t *vals = d.data + d.page_off[(size_t)q.col_index[0] * d.n_segments + seg] + 6;
+    const uint32_t b_first = bucket_of(t0 + (int64_t)r_lo * dt, q.start, q.interval), b_last = bucket_of(t0 + (int64_t)r_hi * dt, q.start, q.interval);
+    const uint32_t nwin = b_last - b_first + 1;
+    for (uint32_t w = lane; w < nwin; w += 32) {
+        const int64_t W0 = q.start + (int64_t)(b_first + w) * q.interval, W1 = W0 + q.interval;
+        /* rows with W0 <= t0 + r*dt < W1, clipped to [r_lo, r_hi] */
+        uint32_t ra = r_lo, rb = r_hi + 1;
+        if (W0 > t0) { uint64_t k = ((uint64_t)(W0 - t0) + dtu - 1) / dtu; if (k > ra) ra = k > rb ? rb : (uint32_t)k; }
+        { uint64_t k = ((uint64_t)(W1 - t0) + dtu - 1) / dtu; if (k < rb) rb = (uint32_t)k; }
+        if (ra >= rb) continue; /* a window without rows (cadence coarser than the interval) */
+        Part parts[OG_MAX_CALLS];
+#pragma unroll
+        for (uint32_t c = 0; c < OG_MAX_CALLS; c++) parts[c] = part_empty();
+        for (uint32_t r = ra; r < rb; r++) {
+            const uint64_t v = ld_le64(vals + 8 * (size_t)r);
+            const int64_t t = t0 + (int64_t)r * dt;
+#pragma unroll
+            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) acc_row(q.calls[c].func, OG_TYPE_FLOAT, parts[c], v, t);
+        }
+        if (w == 0) {
+#pragma unroll
+            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.edges[c], e, parts[c]);
+        } else if (w == nwin - 1) {
+#pragma unroll
+            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.edges[c], e + 1, parts[c]);
+        } else {
+            const size_t ci = (size_t)(series - ch.series_begin) * q.n_buckets + b_first + w;
+#pragma unroll
+            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.cells[c], ci, parts[c]);
+        }
+    }
+    if (lane == 0) { ch.edge_bucket[e] = b_first; ch.edge_bucket[e + 1] = nwin > 1 ? b_last : OG_NO_BUCKET; }
 }
 
 /* 64 bits of the stream at bit position p: rows (p>>5), +1, +2 of the lane's window column */
@@ -174,12 +242,15 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
     const uint32_t n_words = active ? il.grp_words[grp] : 0;
     const uint32_t *src = il.words + (active ? il.grp_off[grp] : 0) + lane; /* word `issued` is at src[0] */
     uint32_t issued = 0;
-    auto refill = [&](uint32_t lim) { /* copy words [issued, lim) */
-        while (issued < lim) {
-            uint32_t r = issued & (NW - 1);
-            cp_async4(col + r * 128, src);
-            if (r < 2) cp_async4(col + (NW + r) * 128, src);
-            src += 32; issued++;
+    auto refill = [&](uint32_t lim) { /* copy whole 8-word batches while they fit below lim (n_words is a multiple of 8) */
+        while (issued + 8 <= lim) {
+            const uint32_t r = issued & (NW - 1), dst = col + r * 128;
+            cp_async4o<0 * 128, 0 * 128>(dst, src); cp_async4o<1 * 128, 1 * 128>(dst, src);
+            cp_async4o<2 * 128, 2 * 128>(dst, src); cp_async4o<3 * 128, 3 * 128>(dst, src);
+            cp_async4o<4 * 128, 4 * 128>(dst, src); cp_async4o<5 * 128, 5 * 128>(dst, src);
+            cp_async4o<6 * 128, 6 * 128>(dst, src); cp_async4o<7 * 128, 7 * 128>(dst, src);
+            if (r == 0) { cp_async4o<NW * 128, 0>(dst, src); cp_async4o<(NW + 1) * 128, 128>(dst, src); } /* mirror rows */
+            src += 8 * 32; issued += 8;
         }
     };
     refill(min(NW, n_words));
@@ -234,7 +305,7 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
 
     /* ---- decode state ---- */
     uint32_t p = 0;          /* bit position of the next unread bit of the lane's stream */
-    uint32_t m = 64, tr = 0, sr = 0, kfast = 0; uint64_t MASK = 0; bool fastok = false, bad = false;
+    uint32_t m = 64, tr = 0, sr = 0, kfast = 0, fast_ctrl = 5, bad = 0; uint64_t MASK = 0;
     bool done = !active;
 
     cp_async_wait<0>();
@@ -247,65 +318,76 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
     uint32_t n_ev = stop; /* rows until the next event (row 0 is current) */
     if (!skipping) { mn = mx = fi = val; n_mn = n_mx = n_ev; }
 
-    /* Refill schedule.  Service s (every K records) copies words up to (p_s>>5) + NW and then waits for the PREVIOUS
-     * service's group, i.e. for words < (p_{s-1}>>5) + NW.  Until service s+1 the lane reads at most 77 + 64 bits past
-     * p_{s+1} <= p_{s-1} + 2*K*77, i.e. words <= (p_{s-1}>>5) + (2*8*77 + 141)/32 + 3 = (p_{s-1}>>5) + 46 < NW. */
+    /* Refill schedule.  Service s (every K records) copies 8-word batches up to (p_s>>5) + NW (so at least up to
+     * (p_s>>5) + NW - 7) and then waits for the PREVIOUS service's group.  Until service s+1 the lane reads at most
+     * 77 + 64 bits past p_{s+1} <= p_{s-1} + 2*K*77, i.e. words <= (p_{s-1}>>5) + (2*8*77 + 141)/32 + 3 = +46 < NW - 7.
+     *
+     * Lanes that are finished (or never were active) keep executing the record decode on whatever their window holds —
+     * it has no side effects — so the hot loop carries no per-lane "done" branch: they have n_ev = 2^32-1 (no event
+     * for 2^32 records), copy nothing (words_lim = 0) and are ignored by the corrupt-page check. */
     constexpr uint32_t K = 8;
-    for (uint32_t it = 0;; it++) {
-        if ((it & (K - 1)) == 0) {
-            if (__all_sync(FULL, done)) break;
-            if (!done && (p >> 5) > n_words) { bad = true; done = true; } /* ran past the stream: corrupt page */
-            if (!done) refill(min((p >> 5) + NW, n_words));
-            cp_async_commit();
-            cp_async_wait<1>();
-        }
-        if (done) continue;
-        if (n_ev == 0) { /* current row == stop */
-            if (skipping) { skipping = false; sum = 0.0; }
-            else {
-                flush(stop, stop > r_hi);
-                if (stop > r_hi) { done = true; continue; }
-                sum = 0.0;
-                while (stop >= rb) { /* advance to the window that contains row `stop` (a loop: dt may exceed the interval) */
-                    cur_b++;
-                    rem += step_r; uint32_t adv = step_q;
-                    if (rem >= dtu) { rem -= dtu; adv++; }
-                    rb = (rb > 0xffffffffu - adv) ? 0xffffffffu : rb + adv;
+    uint32_t words_lim = done ? 0u : n_words;
+    if (done) n_ev = 0xffffffffu;
+    for (;;) {
+        if (__all_sync(FULL, done)) break;
+        if (!done && (p >> 5) > n_words) { bad = 1; done = true; n_ev = 0xffffffffu; words_lim = 0; } /* ran past the stream: corrupt page */
+        refill(min((p >> 5) + NW, words_lim));
+        cp_async_commit();
+        cp_async_wait<1>();
+#pragma unroll 1
+        for (uint32_t k = 0; k < K; k++) {
+            if (n_ev == 0) { /* current row == stop */
+                bool fin = false;
+                if (skipping) { skipping = false; sum = 0.0; }
+                else {
+                    flush(stop, stop > r_hi);
+                    fin = stop > r_hi;
+                    sum = 0.0;
+                    if (!fin) while (stop >= rb) { /* advance to the window that contains row `stop` (a loop: dt may exceed the interval) */
+                        cur_b++;
+                        rem += step_r; uint32_t adv = step_q;
+                        if (rem >= dtu) { rem -= dtu; adv++; }
+                        rb = (rb > 0xffffffffu - adv) ? 0xffffffffu : rb + adv;
+                    }
+                }
+                if (fin) { done = true; n_ev = 0xffffffffu; words_lim = 0; }
+                else {
+                    w_row0 = stop;
+                    uint32_t nstop = rb < r_hi + 1 ? rb : r_hi + 1;
+                    n_ev = nstop - stop; stop = nstop;
+                    mn = mx = fi = val; n_mn = n_mx = n_ev; /* the first value of a window seeds min/max/first (column_util.go:190-278) */
                 }
             }
-            w_row0 = stop;
-            uint32_t nstop = rb < r_hi + 1 ? rb : r_hi + 1;
-            n_ev = nstop - stop; stop = nstop;
-            mn = mx = fi = val; n_mn = n_mx = n_ev; /* the first value of a window seeds min/max/first (column_util.go:190-278) */
-        }
-        /* accumulate the current row */
-        if (FM & FM_SUM) sum = sum + u2d(val);
-        if (FM & FM_MIN) { if (u2d(mn) > u2d(val)) { mn = val; if (TIMES) n_mn = n_ev; } }
-        if (FM & FM_MAX) { if (u2d(mx) < u2d(val)) { mx = val; if (TIMES) n_mx = n_ev; } }
-        if (FM & FM_LAST) lastv = val;
-        n_ev--;
-        /* next record (batch_float.go:352-508) */
-        uint64_t x = fetch64(col, p);
-        uint32_t ctrl = (uint32_t)(x >> 62);
-        if (ctrl == 2 && fastok) { /* '10': reuse the window */
-            val ^= (x >> sr) & MASK;
-            p += kfast;
-        } else if (ctrl < 2) {     /* '0': same value */
-            p += 1;
-        } else {
-            if (ctrl == 3) {       /* '11': 5 bits leading, 6 bits meaningful */
-                uint32_t lm = (uint32_t)(x >> 51) & 0x7ff;
-                uint32_t lead = lm >> 6; m = lm & 0x3f;
-                if (m == 0) { m = 64; tr = 0; } else { if (lead + m > 64) { bad = true; done = true; continue; } tr = 64 - lead - m; }
-                p += 13;
-                fastok = lead >= 2;
-                sr = lead - 2; kfast = 2 + m;
-                MASK = (m == 64 ? ~0ull : ((1ull << m) - 1)) << tr;
-            } else p += 2;
-            uint64_t y = fetch64(col, p);
-            uint64_t sig = m == 64 ? y : (y >> (64 - m));
-            p += m;
-            val ^= sig << tr;
+            /* accumulate the current row */
+            if (FM & FM_SUM) sum = sum + u2d(val);
+            if (FM & FM_MIN) { if (u2d(mn) > u2d(val)) { mn = val; if (TIMES) n_mn = n_ev; } }
+            if (FM & FM_MAX) { if (u2d(mx) < u2d(val)) { mx = val; if (TIMES) n_mx = n_ev; } }
+            if (FM & FM_LAST) lastv = val;
+            n_ev--;
+            /* next record (batch_float.go:352-508) */
+            uint64_t x = fetch64(col, p);
+            uint32_t ctrl = (uint32_t)(x >> 62);
+            if (ctrl == fast_ctrl) {   /* '10' with a window that starts at or below bit 61: reuse it in place */
+                val ^= (x >> sr) & MASK;
+                p += kfast;
+            } else if (ctrl < 2) {     /* '0': same value */
+                p += 1;
+            } else {
+                if (ctrl == 3) {       /* '11': 5 bits leading, 6 bits meaningful */
+                    uint32_t lm = (uint32_t)(x >> 51) & 0x7ff;
+                    uint32_t lead = lm >> 6; m = lm & 0x3f;
+                    if (m == 0) { m = 64; tr = 0; }
+                    else { if (lead + m > 64) { if (!done) bad = 1; lead = 0; m = 64; } tr = 64 - lead - m; }
+                    p += 13;
+                    fast_ctrl = lead >= 2 ? 2u : 5u;
+                    sr = lead - 2; kfast = 2 + m;
+                    MASK = (m == 64 ? ~0ull : ((1ull << m) - 1)) << tr;
+                } else p += 2;
+                uint64_t y = fetch64(col, p);
+                uint64_t sig = m == 64 ? y : (y >> (64 - m));
+                p += m;
+                val ^= sig << tr;
+            }
         }
     }
     if (active) {
