@@ -7,7 +7,7 @@
 Workload (config.workload): BASELINE.json configs[1] — one TSM shard of 10k series x 1M points/series of float64
 (G-hi distribution: 100 + U[0,1) with full mantissa tail -> Gorilla ~6 B/value), 1 s cadence, const-delta time pages,
 1000-row segments; SELECT sum, count (mean) and max GROUP BY time(1m), all series in one tagset.
-A "step" = one og_query_run over the whole HBM-resident shard (one k_fused_segment launch + edge stitch + tagset
+A "step" = one og_query_run over the whole HBM-resident shard (k_fused_fast over the lane-interleaved Gorilla streams, k_fused_raw for raw pages, edge stitch + tagset
 merge).  At N > 1 every rank holds its own shard (distinct seed; configs[3]) and a step ends with the NCCL
 cross-shard merge of the dense bucket arrays (weak scaling).
 
@@ -47,39 +47,73 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe), in-process through NVML
+    (a background thread; og_query_run releases the GIL), falling back to one nvidia-smi query when NVML is missing."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.t, self.h = index, [], False, None, None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        if self.h is not None:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            if not self.rows:
+                self._poll_once()
+            sm = sorted(r[0] for r in self.rows)
+            reasons = sorted({n for r in self.rows for bit, n in names.items() if r[2] & bit})
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[1] for r in self.rows), default=None),
+                    "reasons": reasons, "samples": len(sm), "source": "nvml"}
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.split(",")
+            return {"sm_mhz": int(float(out[0])), "sm_max_mhz": int(float(out[1])), "reasons": [], "samples": 1, "source": "nvidia-smi after the region"}
         except Exception:
-            self.proc.kill()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+
+    def _poll_once(self):
+        self.stop_flag = True
+        try:
+            nv = self.nv
+            self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM), 0))
+        except Exception:
+            pass
+
+
+def ncu_traffic(a):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+    (profiles/traffic.json); only valid for the workload it was captured on, else null."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_fused_fast"]
+        if a.series == 10000 and a.rows == 1000000 and a.dist == "hi":
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def measured_peak():
@@ -223,13 +257,13 @@ def run_ours(a):
     total_rows = rows_t.item()
     value = total_rows * a.steps / (dev_ms_max / 1e3)
 
-    # roofline of the dominant kernel (k_fused_segment): algorithmic bytes per launch / its average duration
+    # roofline of the dominant kernel (k_fused_fast): algorithmic bytes per launch / its average duration
     peak, peak_src = measured_peak()
     algo_bytes = st["page_bytes"] + st["dir_bytes"] + 16667 * 3 * 8  # pages + 32 B/segment directory + dense output
     main_per_launch_ms = main_ms / a.steps
     achieved = algo_bytes / (main_per_launch_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_fused_segment<3>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+    roofline = {"bound": "hbm", "kernel": "k_fused_fast<SUM|COUNT|MAX>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(a), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "bytes_per_row": algo_bytes / max(1, st["rows_decoded"]), "kernel_ms": main_per_launch_ms,
                 "share_of_step": main_ms / max(1e-9, dev_ms if world == 1 else main_ms)}
 
