@@ -34,11 +34,15 @@ struct DirP { /* device directory */
 struct ChunkP { /* one chunk of whole series */
     uint32_t series_begin, series_end; /* global series range */
     uint32_t seg_begin, seg_end;       /* global segment range (contiguous) */
-    Tri cells[OG_MAX_CALLS];           /* [ (series - series_begin) * n_buckets + b ] */
+    Tri cells[OG_MAX_CALLS];           /* [ cell_idx(ch, series, b) ]: bucket-major, series contiguous — a warp whose lanes are
+                                          32 consecutive series writes one bucket as one 256-byte run */
+    uint32_t cell_sb;                  /* cells per bucket row = series of the chunk rounded up to 32 */
     Tri edges[OG_MAX_CALLS];           /* [ 2 * (seg - seg_begin) + {0 head, 1 tail} ] */
     uint32_t *edge_bucket;             /* [ 2 * (seg - seg_begin) ] OG_NO_BUCKET = absent */
     int *err;                          /* [0] first error code, [1] segment */
 };
+
+__device__ __forceinline__ size_t cell_idx(const ChunkP &ch, uint32_t series, uint32_t b) { return (size_t)b * ch.cell_sb + (series - ch.series_begin); }
 
 __device__ __forceinline__ void report_err(int *err, int code, uint32_t seg) {
     if (atomicCAS(&err[0], 0, code) == 0) err[1] = (int)seg;
@@ -202,7 +206,7 @@ __device__ __forceinline__ void emit_window(const QueryP &q, const ChunkP &ch, u
                                             bool is_head, bool is_tail, int call, const Part &p) {
     if (is_head) store_part(ch.edges[call], 2 * (size_t)(seg - ch.seg_begin), p);
     else if (is_tail) store_part(ch.edges[call], 2 * (size_t)(seg - ch.seg_begin) + 1, p);
-    else if (p.ok) store_part(ch.cells[call], (size_t)(series - ch.series_begin) * q.n_buckets + b, p);
+    else if (p.ok) store_part(ch.cells[call], cell_idx(ch, series, b), p);
 }
 
 /* step 3: one warp per segment, one lane per window of that segment; rows of a window are walked in order so
@@ -278,7 +282,7 @@ __global__ void k_fix_edges(DirP d, QueryP q, ChunkP ch) {
                     if (eb[ne + 1] != OG_NO_BUCKET) break; /* that segment has a distinct tail window: run ends at its head */
                 }
             }
-            if (acc.ok) store_part(ch.cells[c], (size_t)(series - ch.series_begin) * q.n_buckets + b, acc);
+            if (acc.ok) store_part(ch.cells[c], cell_idx(ch, series, b), acc);
         }
     }
 }
@@ -321,7 +325,7 @@ __global__ void k_merge_groups(QueryP q, ChunkP ch, GroupP gp) {
                 uint32_t ii = i + u;
                 uint32_t s = ii < hi ? gp.grp_series[ii] : 0xffffffffu;
                 bool in = s < ch.series_end;
-                size_t ci = in ? (size_t)(s - ch.series_begin) * q.n_buckets + b : 0;
+                size_t ci = in ? cell_idx(ch, s, b) : 0;
                 okv[u] = in ? cells.ok[ci] : 0;
                 vv[u] = in ? cells.val[ci] : 0;
                 tt[u] = (in && cells.tim) ? cells.tim[ci] : 0;
@@ -335,6 +339,44 @@ __global__ void k_merge_groups(QueryP q, ChunkP ch, GroupP gp) {
         }
         store_part(gp.dense[c], idx, acc);
     }
+}
+
+/* k_merge_groups for the one-tagset case (OG_GROUP_ALL) when no call carries a time: the cell matrix is bucket-major with
+ * the series contiguous, so a block stages a [128 buckets][32 series] tile through shared memory with fully coalesced 256-byte
+ * row loads, then thread t folds row t left to right — the same strictly sequential series order as k_merge_groups. */
+__global__ void __launch_bounds__(128) k_merge_all(QueryP q, ChunkP ch, GroupP gp) {
+    __shared__ uint64_t sv[128 * 33];
+    __shared__ uint8_t sk[128 * 36];
+    const uint32_t c = blockIdx.y, b0 = blockIdx.x * 128, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const uint32_t nS = ch.series_end - ch.series_begin, nb = q.n_buckets;
+    const CallP &cp = q.calls[c];
+    const int ftype = cp.out_type == OG_TYPE_INT && cp.func == OG_AGG_COUNT ? OG_TYPE_INT : cp.type;
+    const Tri cells = ch.cells[c];
+    Part acc = part_empty();
+    if (b0 + t < nb) acc = load_part(gp.dense[c], b0 + t);
+    for (uint32_t s0 = 0; s0 < nS; s0 += 32) {
+        const uint32_t sr = s0 + lane;
+#pragma unroll 8
+        for (uint32_t i = 0; i < 32; i++) {
+            const uint32_t r = w + 4 * i, b = b0 + r;
+            const bool in = b < nb && sr < nS;
+            const size_t ci = in ? (size_t)b * ch.cell_sb + sr : 0;
+            const uint8_t k = in ? cells.ok[ci] : (uint8_t)0;
+            sv[r * 33 + lane] = in ? cells.val[ci] : 0;
+            sk[r * 36 + lane] = k;
+        }
+        __syncthreads();
+        if (b0 + t < nb) {
+#pragma unroll 8
+            for (uint32_t k = 0; k < 32; k++) {
+                if (!sk[t * 36 + k]) continue;
+                Part p; p.ok = 1; p.v = sv[t * 33 + k]; p.t = 0;
+                group_update(cp.func, ftype, q.multi != 0, acc, p);
+            }
+        }
+        __syncthreads();
+    }
+    if (b0 + t < nb) store_part(gp.dense[c], b0 + t, acc);
 }
 
 /* dense initialisation: values 0, valid 0, times = window start (single-call selectors) or 0 (RecMeta.Times) */

@@ -133,7 +133,7 @@ OG_API void og_shard_close(og_shard *s) {
     cudaFree(s->d_page_off); cudaFree(s->d_page_len); cudaFree(s->d_sids);
     if (s->h_seg_buf) cudaFreeHost(s->h_seg_buf);
     if (s->d_seg_buf) cudaFree(s->d_seg_buf);
-    for (auto &c : s->il) { cudaFree(c.words); cudaFree(c.grp_off); cudaFree(c.grp_words); cudaFree(c.ok); }
+    for (auto &c : s->il) { cudaFree(c.words); cudaFree(c.grp_off); cudaFree(c.grp_words); cudaFree(c.ok); cudaFree(c.lane_seg); }
     delete s;
 }
 
@@ -357,7 +357,7 @@ struct Plan { /* built once per query, reused by every og_query_run */
     bool fused;
     uint8_t *cls;   /* per-segment class (SEG_FAST / SEG_GENERAL) when the fast Gorilla kernel applies, else nullptr */
     int fm; bool times;
-    IlP il;
+    IlP il; uint32_t il_groups, il_J;
     uint32_t *cls_list[2];              /* device: sorted ids of the SEG_GENERAL [0] / SEG_RAW [1] segments (k_fused_segment / k_fused_raw) */
     std::vector<uint32_t> *cls_host[2]; /* same, on the host (per-chunk ranges are found by binary search) */
 };
@@ -367,13 +367,17 @@ template <class T> int salloc(og_query *q, T **p, size_t n) { int rc = dalloc(p,
 template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP &ch, const uint32_t *list, uint32_t n, cudaStream_t st) {
     if (n) k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch, list, n);
 }
-struct FastArgs { IlP il; };
+struct FastArgs { IlP il; uint32_t n_groups, segs_per_series; };
 template <int FM, bool TIMES> void launch_fast_t(const FastArgs &fa, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
-    /* lane groups are absolute (segment / 32); a group that straddles the chunk boundary runs with the lanes of this chunk */
-    uint32_t g0 = ch.seg_begin / 32, g1 = (ch.seg_end + 31) / 32;
+    /* lane groups of this chunk: 32-series blocks x segment index on regular shards (chunks are multiples of 32 series),
+     * else 32 consecutive segments (a group that straddles the chunk boundary runs with the lanes of this chunk) */
+    uint32_t g0, g1;
+    if (fa.segs_per_series) { g0 = (ch.series_begin / 32) * fa.segs_per_series; g1 = ((ch.series_end + 31) / 32) * fa.segs_per_series; }
+    else { g0 = ch.seg_begin / 32; g1 = (ch.seg_end + 31) / 32; }
+    g1 = std::min(g1, fa.n_groups);
     constexpr uint32_t WPB = OG_FAST_THREADS / 32;
     dim3 grid((g1 - g0 + WPB - 1) / WPB), block(OG_FAST_THREADS);
-    k_fused_fast<FM, TIMES><<<grid, block, 0, st>>>(d, p, ch, cls, fa.il, g0);
+    k_fused_fast<FM, TIMES><<<grid, block, 0, st>>>(d, p, ch, cls, fa.il, g0, g1);
 }
 /* a handful of aggregate-set specialisations; anything else runs the all-aggregates instance */
 void launch_fast(int fm, bool times, const FastArgs &stage, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
@@ -403,7 +407,21 @@ int ensure_il(og_shard *s, int col, cudaStream_t st) {
     if (ic.state != 0) return OG_OK;
     ic.state = -1;
     if (s->n_segments == 0 || s->col_types[col] != OG_TYPE_FLOAT) return OG_OK;
-    const uint32_t ng = (s->n_segments + 31) / 32;
+    /* lane groups: segment j of 32 consecutive series when every series has the same number of segments, else 32 consecutive segments */
+    uint32_t J = s->n_series ? s->h_series_seg_begin[1] - s->h_series_seg_begin[0] : 0;
+    for (uint32_t i = 0; i < s->n_series && J; i++) if (s->h_series_seg_begin[i + 1] - s->h_series_seg_begin[i] != J) J = 0;
+    const uint32_t ng = J ? ((s->n_series + 31) / 32) * J : (s->n_segments + 31) / 32;
+    {
+        std::vector<uint32_t> ls((size_t)ng * 32, OG_IL_NONE);
+        if (J) {
+            for (uint32_t sr = 0; sr < s->n_series; sr++)
+                for (uint32_t j = 0; j < J; j++) ls[((size_t)(sr / 32) * J + j) * 32 + (sr & 31)] = s->h_series_seg_begin[sr] + j;
+        } else for (uint32_t g = 0; g < s->n_segments; g++) ls[g] = g;
+        int rc0;
+        if ((rc0 = dalloc(&ic.lane_seg, ls.size()))) return rc0;
+        CU(cudaMemcpy(ic.lane_seg, ls.data(), ls.size() * 4, cudaMemcpyHostToDevice));
+    }
+    ic.n_groups = ng; ic.segs_per_series = J;
     uint32_t *seg_words = nullptr;
     int rc;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -414,7 +432,7 @@ int ensure_il(og_shard *s, int col, cudaStream_t st) {
     if ((rc = dalloc(&ic.grp_off, (size_t)ng))) { cudaFree(seg_words); return rc; }
     DirP d = make_dir(s);
     k_il_scan<<<(s->n_segments + 255) / 256, 256, 0, st>>>(d, col, s->col_types[col], ic.ok, seg_words);
-    k_il_group_words<<<(ng * 32 + 255) / 256, 256, 0, st>>>(s->n_segments, seg_words, ic.grp_words);
+    k_il_group_words<<<(unsigned)(((size_t)ng * 32 + 255) / 256), 256, 0, st>>>(ng, ic.lane_seg, seg_words, ic.grp_words);
     std::vector<uint32_t> gw(ng); std::vector<uint64_t> go(ng);
     CU(cudaMemcpyAsync(gw.data(), ic.grp_words, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -427,7 +445,7 @@ int ensure_il(og_shard *s, int col, cudaStream_t st) {
     if (total * 4 + ((size_t)8 << 30) > free_b) return OG_OK; /* keep headroom for the query scratch: fall back to the general kernel */
     if (cudaMalloc(&ic.words, total * 4) != cudaSuccess) { cudaGetLastError(); ic.words = nullptr; return OG_OK; }
     CU(cudaMemcpyAsync(ic.grp_off, go.data(), (size_t)ng * 8, cudaMemcpyHostToDevice, st));
-    k_il_repack<<<(ng * 32 + 127) / 128, 128, 0, st>>>(d, col, ic.ok, ic.grp_off, ic.grp_words, ng, ic.words);
+    k_il_repack<<<(unsigned)(((size_t)ng * 32 + 127) / 128), 128, 0, st>>>(d, col, ic.ok, ic.lane_seg, ic.grp_off, ic.grp_words, ng, ic.words);
     CU(cudaGetLastError());
     cudaEventRecord(e1, st);
     CU(cudaStreamSynchronize(st));
@@ -479,6 +497,7 @@ int build_plan(og_query *q) {
     CU(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
     q->chunk_series = (uint32_t)std::max<size_t>(1, std::min<size_t>(s->n_series, budget / std::max<size_t>(1, cell_bytes_per_series)));
+    if (q->chunk_series < s->n_series) q->chunk_series = std::max<uint32_t>(32, q->chunk_series & ~31u); /* lane groups of 32 series never straddle chunks */
     uint32_t max_chunk_segs = 0;
     for (uint32_t a = 0; a < s->n_series; a += q->chunk_series) {
         uint32_t b = std::min(s->n_series, a + q->chunk_series);
@@ -486,7 +505,8 @@ int build_plan(og_query *q) {
     }
     ChunkP &ch = pl->ch;
     ch.err = q->d_err;
-    size_t chunk_cells = (size_t)q->chunk_series * p.n_buckets;
+    ch.cell_sb = (q->chunk_series + 31) & ~31u;
+    size_t chunk_cells = (size_t)ch.cell_sb * p.n_buckets;
     for (uint32_t c = 0; c < p.n_calls; c++) {
         bool sel = p.calls[c].func >= OG_AGG_MIN;
         if ((rc = salloc(q, &ch.cells[c].val, chunk_cells))) return rc;
@@ -506,7 +526,8 @@ int build_plan(og_query *q) {
     }
     if (pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments && s->il[p.col_index[0]].state == 1) {
         const og_shard::IlCol &ic = s->il[p.col_index[0]];
-        pl->il.words = ic.words; pl->il.grp_off = ic.grp_off; pl->il.grp_words = ic.grp_words; pl->il.ok = ic.ok;
+        pl->il.words = ic.words; pl->il.grp_off = ic.grp_off; pl->il.grp_words = ic.grp_words; pl->il.ok = ic.ok; pl->il.lane_seg = ic.lane_seg;
+        pl->il_groups = ic.n_groups; pl->il_J = ic.segs_per_series;
         if ((rc = salloc(q, &pl->cls, (size_t)s->n_segments))) return rc;
         k_classify<<<(s->n_segments + 255) / 256, 256, 0, st>>>(make_dir(s), p, ic.ok, pl->cls);
         CU(cudaGetLastError());
@@ -584,10 +605,10 @@ OG_API int og_query_run(og_query *q) {
         uint32_t nseg = ch.seg_end - ch.seg_begin;
         if (nseg == 0) continue;
         segs_scanned += nseg;
-        for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)(b - a) * p.n_buckets, st));
+        for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)ch.cell_sb * p.n_buckets, st));
         CU(cudaEventRecord(q->main_ev[2 * chunks_run], st));
         if (pl->fused) {
-            if (pl->cls) { launch_fast(pl->fm, pl->times, FastArgs{pl->il}, dir, p, ch, pl->cls, st); launches++; }
+            if (pl->cls) { launch_fast(pl->fm, pl->times, FastArgs{pl->il, pl->il_groups, pl->il_J}, dir, p, ch, pl->cls, st); launches++; }
             const uint32_t *gl = nullptr; uint32_t gn = nseg;
             if (pl->cls) { /* leftovers of this chunk: a contiguous range of each sorted list */
                 auto range = [&](int k, const uint32_t **l, uint32_t *cnt) {
@@ -626,7 +647,10 @@ OG_API int og_query_run(og_query *q) {
         CU(cudaEventRecord(q->main_ev[2 * chunks_run + 1], st));
         chunks_run++;
         k_fix_edges<<<(nseg + 127) / 128, 128, 0, st>>>(dir, p, ch);
-        k_merge_groups<<<dim3((unsigned)((cells_dense + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp);
+        bool any_tim = false;
+        for (uint32_t c = 0; c < p.n_calls; c++) any_tim |= gp.dense[c].tim != nullptr;
+        if (q->desc.group_mode == OG_GROUP_ALL && !any_tim) k_merge_all<<<dim3((p.n_buckets + 127) / 128, p.n_calls), 128, 0, st>>>(p, ch, gp);
+        else k_merge_groups<<<dim3((unsigned)((cells_dense + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp);
         launches += 2;
     }
     CU(cudaEventRecord(q->ev1, st));

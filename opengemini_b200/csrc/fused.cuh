@@ -62,7 +62,7 @@ struct FusedState {
 #pragma unroll
             for (int c = 0; c < NC; c++) store_part(ch.edges[c], e + 1, parts[c]);
         } else {
-            size_t ci = (size_t)(series - ch.series_begin) * q.n_buckets + cur_b;
+            size_t ci = cell_idx(ch, series, cur_b);
 #pragma unroll
             for (int c = 0; c < NC; c++) if (parts[c].ok) store_part(ch.cells[c], ci, parts[c]);
         }

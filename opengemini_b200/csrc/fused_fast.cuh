@@ -48,8 +48,16 @@ enum { FM_COUNT = 1, FM_SUM = 2, FM_MIN = 4, FM_MAX = 8, FM_FIRST = 16, FM_LAST 
 enum { SEG_GENERAL = 0, SEG_FAST = 1, SEG_RAW = 2 };  /* per-segment classes computed by k_classify */
 
 #define OG_FAST_THREADS 128
+#ifndef OG_IL_NW
 #define OG_IL_NW 64u            /* window rows (words per lane) */
-#define OG_IL_ROWS 66u          /* + 2 mirror rows: rows 64,65 repeat rows 0,1 so that three consecutive rows never wrap */
+#endif
+#define OG_IL_ROWS (OG_IL_NW + 2u) /* + 2 mirror rows that repeat rows 0,1 so that three consecutive rows never wrap */
+#ifndef OG_IL_K
+#define OG_IL_K 8u              /* records between two refills */
+#endif
+#ifndef OG_IL_BATCH
+#define OG_IL_BATCH 8u          /* words per refill batch (4 or 8) */
+#endif
 #define OG_IL_PAD_WORDS 6u      /* words appended to every stream: the decoder may touch 77 + 64 bits past the last record */
 #define OG_IL_HDR 7u            /* page = [31][rows u32][0x30][0x10] | stream: first value 8 B BE, records... */
 
@@ -58,8 +66,14 @@ struct IlP {
     const uint32_t *words;     /* il[grp_off[g] + w*32 + lane] */
     const uint64_t *grp_off;   /* [n_groups32] in words */
     const uint32_t *grp_words; /* [n_groups32] words per lane in this group (0: no eligible lane) */
-    const uint8_t *ok;         /* [n_segments] static eligibility (codec + header shape) */
+    const uint8_t *ok;         /* [n_segments] static class (SEG_*) by codec + header shape */
+    const uint32_t *lane_seg;  /* [n_groups32 * 32] segment of every lane slot, OG_IL_NONE = empty.  Regular shards (every
+                                  series has the same number of segments) put segment j of 32 CONSECUTIVE SERIES in one group:
+                                  the lanes then share window boundaries (flushes coincide, no divergence) and write one
+                                  bucket of 32 consecutive series = one 256-byte run of the cell matrix.  Otherwise a group
+                                  is 32 consecutive segments. */
 };
+#define OG_IL_NONE 0xffffffffu
 
 /* static eligibility + stream length in words (one thread per segment; header bytes only) */
 __global__ void k_il_scan(DirP d, int col, int col_type, uint8_t *ok, uint32_t *seg_words) {
@@ -87,24 +101,25 @@ __global__ void k_il_scan(DirP d, int col, int col_type, uint8_t *ok, uint32_t *
 }
 
 /* words per lane of every lane group = max over its eligible lanes (one warp per group) */
-__global__ void k_il_group_words(uint32_t n_segments, const uint32_t *seg_words, uint32_t *grp_words) {
+__global__ void k_il_group_words(uint32_t n_groups, const uint32_t *lane_seg, const uint32_t *seg_words, uint32_t *grp_words) {
     uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    uint32_t seg = g * 32 + lane;
-    uint32_t w = seg < n_segments ? seg_words[seg] : 0;
+    if (g >= n_groups) return;
+    uint32_t seg = lane_seg[(size_t)g * 32 + lane];
+    uint32_t w = seg != OG_IL_NONE ? seg_words[seg] : 0;
 #pragma unroll
     for (int o = 16; o; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
-    if (lane == 0 && g * 32 < n_segments) grp_words[g] = w;
+    if (lane == 0) grp_words[g] = w;
 }
 
 /* the repack: word w of lane l -> il[grp_off + w*32 + l], big-endian stream words stored in native order (one warp per group) */
-__global__ void k_il_repack(DirP d, int col, const uint8_t *ok, const uint64_t *grp_off, const uint32_t *grp_words, uint32_t n_groups,
-                            uint32_t *il) {
+__global__ void k_il_repack(DirP d, int col, const uint8_t *ok, const uint32_t *lane_seg, const uint64_t *grp_off, const uint32_t *grp_words,
+                            uint32_t n_groups, uint32_t *il) {
     uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g >= n_groups) return;
     uint32_t nw = grp_words[g];
     if (nw == 0) return;
-    uint32_t seg = g * 32 + lane;
-    bool live = seg < d.n_segments && ok[seg] == SEG_FAST;
+    uint32_t seg = lane_seg[(size_t)g * 32 + lane];
+    bool live = seg != OG_IL_NONE && ok[seg] == SEG_FAST;
     const uint32_t *base = nullptr; uint32_t sh = 0, own_words = 0;
     if (live) {
         size_t pi = (size_t)col * d.n_segments + seg;
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(128) k_fused_raw(DirP d, QueryP q, ChunkP ch, 
 #pragma unroll
             for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.edges[c], e + 1, parts[c]);
         } else {
-            const size_t ci = (size_t)(series - ch.series_begin) * q.n_buckets + b_first + w;
+            const size_t ci = cell_idx(ch, series, b_first + w);
 #pragma unroll
             for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.cells[c], ci, parts[c]);
         }
@@ -207,16 +222,16 @@ __device__ __forceinline__ uint64_t fetch64(uint32_t col, uint32_t p) {
 }
 
 template <int FM, bool TIMES>
-__global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q, ChunkP ch, const uint8_t *cls, IlP il, uint32_t grp_begin) {
+__global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q, ChunkP ch, const uint8_t *cls, IlP il, uint32_t grp_begin, uint32_t grp_end) {
     constexpr uint32_t NW = OG_IL_NW;
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ __align__(128) uint32_t s_win[(OG_FAST_THREADS / 32) * OG_IL_ROWS * 32];
 
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t grp = grp_begin + blockIdx.x * (OG_FAST_THREADS / 32) + wid;
-    const uint32_t seg = grp * 32 + lane;
+    const uint32_t seg = grp < grp_end ? il.lane_seg[(size_t)grp * 32 + lane] : OG_IL_NONE;
     /* a lane group that straddles two chunks runs in both, with complementary lanes */
-    bool active = seg >= ch.seg_begin && seg < ch.seg_end && cls[seg] == SEG_FAST;
+    bool active = seg != OG_IL_NONE && seg >= ch.seg_begin && seg < ch.seg_end && cls[seg] == SEG_FAST;
     if (!__any_sync(FULL, active)) return;
     const size_t e = 2 * (size_t)(seg - ch.seg_begin);
 
@@ -242,15 +257,17 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
     const uint32_t n_words = active ? il.grp_words[grp] : 0;
     const uint32_t *src = il.words + (active ? il.grp_off[grp] : 0) + lane; /* word `issued` is at src[0] */
     uint32_t issued = 0;
-    auto refill = [&](uint32_t lim) { /* copy whole 8-word batches while they fit below lim (n_words is a multiple of 8) */
-        while (issued + 8 <= lim) {
+    auto refill = [&](uint32_t lim) { /* copy whole batches while they fit below lim (n_words is a multiple of 8) */
+        while (issued + OG_IL_BATCH <= lim) {
             const uint32_t r = issued & (NW - 1), dst = col + r * 128;
             cp_async4o<0 * 128, 0 * 128>(dst, src); cp_async4o<1 * 128, 1 * 128>(dst, src);
             cp_async4o<2 * 128, 2 * 128>(dst, src); cp_async4o<3 * 128, 3 * 128>(dst, src);
+#if OG_IL_BATCH == 8
             cp_async4o<4 * 128, 4 * 128>(dst, src); cp_async4o<5 * 128, 5 * 128>(dst, src);
             cp_async4o<6 * 128, 6 * 128>(dst, src); cp_async4o<7 * 128, 7 * 128>(dst, src);
+#endif
             if (r == 0) { cp_async4o<NW * 128, 0>(dst, src); cp_async4o<(NW + 1) * 128, 128>(dst, src); } /* mirror rows */
-            src += 8 * 32; issued += 8;
+            src += OG_IL_BATCH * 32; issued += OG_IL_BATCH;
         }
     };
     refill(min(NW, n_words));
@@ -297,7 +314,7 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
 #pragma unroll
             for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.edges[c], e + 1, part_of(q.calls[c].func, stop, cnt));
         } else {
-            size_t ci = (size_t)(series - ch.series_begin) * q.n_buckets + cur_b;
+            size_t ci = cell_idx(ch, series, cur_b);
 #pragma unroll
             for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.cells[c], ci, part_of(q.calls[c].func, stop, cnt));
         }
@@ -325,7 +342,8 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
      * Lanes that are finished (or never were active) keep executing the record decode on whatever their window holds —
      * it has no side effects — so the hot loop carries no per-lane "done" branch: they have n_ev = 2^32-1 (no event
      * for 2^32 records), copy nothing (words_lim = 0) and are ignored by the corrupt-page check. */
-    constexpr uint32_t K = 8;
+    constexpr uint32_t K = OG_IL_K;
+    static_assert((2 * K * 77 + 13) / 32 + 4 <= OG_IL_NW - OG_IL_BATCH + 1, "window too small for the refill period");
     uint32_t words_lim = done ? 0u : n_words;
     if (done) n_ev = 0xffffffffu;
     for (;;) {

@@ -52,6 +52,7 @@ struct og_shard {
     /* lane-interleaved stream copy per column for the fast Gorilla kernel (fused_fast.cuh), built on first use */
     struct IlCol { int state = 0; /* 0 not built, 1 ready, -1 unavailable (no eligible segment / out of memory) */
                    uint32_t *words = nullptr; uint64_t *grp_off = nullptr; uint32_t *grp_words = nullptr; uint8_t *ok = nullptr;
+                   uint32_t *lane_seg = nullptr; uint32_t n_groups = 0, segs_per_series = 0; /* segs_per_series != 0: lanes = 32 consecutive series */
                    uint64_t n_words = 0; double build_ms = 0; };
     std::vector<IlCol> il; /* [n_columns] */
 };
