@@ -49,14 +49,14 @@ enum { SEG_GENERAL = 0, SEG_FAST = 1, SEG_RAW = 2 };  /* per-segment classes com
 
 #define OG_FAST_THREADS 128
 #ifndef OG_IL_NW
-#define OG_IL_NW 64u            /* window rows (words per lane) */
+#define OG_IL_NW 32u            /* window rows (words per lane) */
 #endif
 #define OG_IL_ROWS (OG_IL_NW + 2u) /* + 2 mirror rows that repeat rows 0,1 so that three consecutive rows never wrap */
 #ifndef OG_IL_K
-#define OG_IL_K 8u              /* records between two refills */
+#define OG_IL_K 4u              /* records between two refills */
 #endif
 #ifndef OG_IL_BATCH
-#define OG_IL_BATCH 8u          /* words per refill batch (4 or 8) */
+#define OG_IL_BATCH 4u          /* words per refill batch (4 or 8) */
 #endif
 #define OG_IL_PAD_WORDS 6u      /* words appended to every stream: the decoder may touch 77 + 64 bits past the last record */
 #define OG_IL_HDR 7u            /* page = [31][rows u32][0x30][0x10] | stream: first value 8 B BE, records... */
@@ -304,20 +304,16 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
         }
         return pp;
     };
-    auto flush = [&](uint32_t stop, bool final) { /* the window [w_row0, stop) */
-        uint32_t cnt = stop - w_row0;
-        if (!head_done) {
-#pragma unroll
-            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.edges[c], e, part_of(q.calls[c].func, stop, cnt));
-            head_done = true; head_b = cur_b;
-        } else if (final) {
-#pragma unroll
-            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.edges[c], e + 1, part_of(q.calls[c].func, stop, cnt));
-        } else {
-            size_t ci = cell_idx(ch, series, cur_b);
-#pragma unroll
-            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.cells[c], ci, part_of(q.calls[c].func, stop, cnt));
+    auto flush = [&](uint32_t stop, bool final) { /* the window [w_row0, stop): head edge, tail edge or an interior cell */
+        const uint32_t cnt = stop - w_row0;
+        const int kind = !head_done ? 0 : final ? 1 : 2;
+        const size_t idx = kind == 2 ? cell_idx(ch, series, cur_b) : e + kind;
+#pragma unroll 1
+        for (uint32_t c = 0; c < q.n_calls; c++) { /* rolled on purpose: this path runs once per window, keep it small */
+            const Tri &dst = kind == 2 ? ch.cells[c] : ch.edges[c];
+            store_part(dst, idx, part_of(q.calls[c].func, stop, cnt));
         }
+        if (kind == 0) { head_done = true; head_b = cur_b; }
     };
 
     /* ---- decode state ---- */
@@ -352,7 +348,7 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
         refill(min((p >> 5) + NW, words_lim));
         cp_async_commit();
         cp_async_wait<1>();
-#pragma unroll 1
+#pragma unroll 2
         for (uint32_t k = 0; k < K; k++) {
             if (n_ev == 0) { /* current row == stop */
                 bool fin = false;
