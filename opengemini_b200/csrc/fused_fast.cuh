@@ -342,65 +342,76 @@ __global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q
     static_assert((2 * K * 77 + 13) / 32 + 4 <= OG_IL_NW - OG_IL_BATCH + 1, "window too small for the refill period");
     uint32_t words_lim = done ? 0u : n_words;
     if (done) n_ev = 0xffffffffu;
+    auto on_event = [&]() {
+        bool fin = false;
+        if (skipping) { skipping = false; sum = 0.0; }
+        else {
+            flush(stop, stop > r_hi);
+            fin = stop > r_hi;
+            sum = 0.0;
+            if (!fin) while (stop >= rb) { /* advance to the window that contains row `stop` (a loop: dt may exceed the interval) */
+                cur_b++;
+                rem += step_r; uint32_t adv = step_q;
+                if (rem >= dtu) { rem -= dtu; adv++; }
+                rb = (rb > 0xffffffffu - adv) ? 0xffffffffu : rb + adv;
+            }
+        }
+        if (fin) { done = true; n_ev = 0xffffffffu; words_lim = 0; }
+        else {
+            w_row0 = stop;
+            uint32_t nstop = rb < r_hi + 1 ? rb : r_hi + 1;
+            n_ev = nstop - stop; stop = nstop;
+            mn = mx = fi = val; n_mn = n_mx = n_ev; /* the first value of a window seeds min/max/first (column_util.go:190-278) */
+        }
+    };
+    auto record = [&]() {
+        /* accumulate the current row */
+        if (FM & FM_SUM) sum = sum + u2d(val);
+        if (FM & FM_MIN) { if (u2d(mn) > u2d(val)) { mn = val; if (TIMES) n_mn = n_ev; } }
+        if (FM & FM_MAX) { if (u2d(mx) < u2d(val)) { mx = val; if (TIMES) n_mx = n_ev; } }
+        if (FM & FM_LAST) lastv = val;
+        n_ev--;
+        /* next record (batch_float.go:352-508) */
+        uint64_t x = fetch64(col, p);
+        uint32_t ctrl = (uint32_t)(x >> 62);
+        if (ctrl == fast_ctrl) {   /* '10' with a window that starts at or below bit 61: reuse it in place */
+            val ^= (x >> sr) & MASK;
+            p += kfast;
+        } else if (ctrl < 2) {     /* '0': same value */
+            p += 1;
+        } else {
+            if (ctrl == 3) {       /* '11': 5 bits leading, 6 bits meaningful */
+                uint32_t lm = (uint32_t)(x >> 51) & 0x7ff;
+                uint32_t lead = lm >> 6; m = lm & 0x3f;
+                if (m == 0) { m = 64; tr = 0; }
+                else { if (lead + m > 64) { if (!done) bad = 1; lead = 0; m = 64; } tr = 64 - lead - m; }
+                p += 13;
+                fast_ctrl = lead >= 2 ? 2u : 5u;
+                sr = lead - 2; kfast = 2 + m;
+                MASK = (m == 64 ? ~0ull : ((1ull << m) - 1)) << tr;
+            } else p += 2;
+            uint64_t y = fetch64(col, p);
+            uint64_t sig = m == 64 ? y : (y >> (64 - m));
+            p += m;
+            val ^= sig << tr;
+        }
+    };
     for (;;) {
         if (__all_sync(FULL, done)) break;
         if (!done && (p >> 5) > n_words) { bad = 1; done = true; n_ev = 0xffffffffu; words_lim = 0; } /* ran past the stream: corrupt page */
         refill(min((p >> 5) + NW, words_lim));
         cp_async_commit();
         cp_async_wait<1>();
+        /* When no lane reaches a window boundary within the next K records (lanes of a regular shard are in lockstep, so
+         * this is 14 rounds out of 15 at 60 rows per window) the records run without the per-record event test. */
+        if (__reduce_min_sync(FULL, n_ev) >= K) {
 #pragma unroll 2
-        for (uint32_t k = 0; k < K; k++) {
-            if (n_ev == 0) { /* current row == stop */
-                bool fin = false;
-                if (skipping) { skipping = false; sum = 0.0; }
-                else {
-                    flush(stop, stop > r_hi);
-                    fin = stop > r_hi;
-                    sum = 0.0;
-                    if (!fin) while (stop >= rb) { /* advance to the window that contains row `stop` (a loop: dt may exceed the interval) */
-                        cur_b++;
-                        rem += step_r; uint32_t adv = step_q;
-                        if (rem >= dtu) { rem -= dtu; adv++; }
-                        rb = (rb > 0xffffffffu - adv) ? 0xffffffffu : rb + adv;
-                    }
-                }
-                if (fin) { done = true; n_ev = 0xffffffffu; words_lim = 0; }
-                else {
-                    w_row0 = stop;
-                    uint32_t nstop = rb < r_hi + 1 ? rb : r_hi + 1;
-                    n_ev = nstop - stop; stop = nstop;
-                    mn = mx = fi = val; n_mn = n_mx = n_ev; /* the first value of a window seeds min/max/first (column_util.go:190-278) */
-                }
-            }
-            /* accumulate the current row */
-            if (FM & FM_SUM) sum = sum + u2d(val);
-            if (FM & FM_MIN) { if (u2d(mn) > u2d(val)) { mn = val; if (TIMES) n_mn = n_ev; } }
-            if (FM & FM_MAX) { if (u2d(mx) < u2d(val)) { mx = val; if (TIMES) n_mx = n_ev; } }
-            if (FM & FM_LAST) lastv = val;
-            n_ev--;
-            /* next record (batch_float.go:352-508) */
-            uint64_t x = fetch64(col, p);
-            uint32_t ctrl = (uint32_t)(x >> 62);
-            if (ctrl == fast_ctrl) {   /* '10' with a window that starts at or below bit 61: reuse it in place */
-                val ^= (x >> sr) & MASK;
-                p += kfast;
-            } else if (ctrl < 2) {     /* '0': same value */
-                p += 1;
-            } else {
-                if (ctrl == 3) {       /* '11': 5 bits leading, 6 bits meaningful */
-                    uint32_t lm = (uint32_t)(x >> 51) & 0x7ff;
-                    uint32_t lead = lm >> 6; m = lm & 0x3f;
-                    if (m == 0) { m = 64; tr = 0; }
-                    else { if (lead + m > 64) { if (!done) bad = 1; lead = 0; m = 64; } tr = 64 - lead - m; }
-                    p += 13;
-                    fast_ctrl = lead >= 2 ? 2u : 5u;
-                    sr = lead - 2; kfast = 2 + m;
-                    MASK = (m == 64 ? ~0ull : ((1ull << m) - 1)) << tr;
-                } else p += 2;
-                uint64_t y = fetch64(col, p);
-                uint64_t sig = m == 64 ? y : (y >> (64 - m));
-                p += m;
-                val ^= sig << tr;
+            for (uint32_t k = 0; k < K; k++) record();
+        } else {
+#pragma unroll 1
+            for (uint32_t k = 0; k < K; k++) {
+                if (n_ev == 0) on_event(); /* current row == stop */
+                record();
             }
         }
     }
