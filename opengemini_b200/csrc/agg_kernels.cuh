@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(128) k_merge_all(QueryP q, ChunkP ch, GroupP g
     if (b0 + t < nb) acc = load_part(gp.dense[c], b0 + t);
     for (uint32_t s0 = 0; s0 < nS; s0 += 32) {
         const uint32_t sr = s0 + lane;
-#pragma unroll 8
+#pragma unroll 16
         for (uint32_t i = 0; i < 32; i++) {
             const uint32_t r = w + 4 * i, b = b0 + r;
             const bool in = b < nb && sr < nS;

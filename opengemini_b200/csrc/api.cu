@@ -619,7 +619,14 @@ OG_API int og_query_run(og_query *q) {
                 range(0, &gl, &gn);
                 const uint32_t *rl; uint32_t rn;
                 range(1, &rl, &rn);
-                if (rn) { k_fused_raw<<<(rn * 32 + 127) / 128, 128, 0, st>>>(dir, p, ch, rl, rn); launches++; }
+                if (rn) { /* instances by whether min/max need row times and whether a sum is asked for */
+                    const unsigned gb = (rn * 32 + 127) / 128;
+                    const bool need_sum = (pl->fm & FM_SUM) != 0;
+                    if (pl->times) k_fused_raw<63, true><<<gb, 128, 0, st>>>(dir, p, ch, rl, rn);
+                    else if (need_sum) k_fused_raw<FM_SUM | FM_MIN | FM_MAX, false><<<gb, 128, 0, st>>>(dir, p, ch, rl, rn);
+                    else k_fused_raw<FM_MIN | FM_MAX, false><<<gb, 128, 0, st>>>(dir, p, ch, rl, rn);
+                    launches++;
+                }
             }
             switch (p.n_calls) {
             case 1: launch_fused<1>(dir, p, ch, gl, gn, st); break;

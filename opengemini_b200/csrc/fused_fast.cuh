@@ -59,6 +59,7 @@ enum { SEG_GENERAL = 0, SEG_FAST = 1, SEG_RAW = 2 };  /* per-segment classes com
 #define OG_IL_BATCH 4u          /* words per refill batch (4 or 8) */
 #endif
 #define OG_IL_PAD_WORDS 6u      /* words appended to every stream: the decoder may touch 77 + 64 bits past the last record */
+#define OG_RAW_STAGE 8208u     /* k_fused_raw staging bytes per warp: 1024 rows + alignment slack */
 #define OG_IL_HDR 7u            /* page = [31][rows u32][0x30][0x10] | stream: first value 8 B BE, records... */
 
 /* lane-interleaved stream copy of one column (owned by the shard, built lazily) */
@@ -164,6 +165,7 @@ __global__ void k_list_class(const uint8_t *cls, uint32_t n_segments, uint8_t kl
 
 /* Raw float pages with const-delta time: every row is addressable, so one warp takes a segment and each lane reduces one
  * window (rows of a window sequentially: float sums keep the reference order).  Same outputs as k_fused_segment. */
+template <int FM, bool TIMES>
 __global__ void __launch_bounds__(128) k_fused_raw(DirP d, QueryP q, ChunkP ch, const uint32_t *list, uint32_t n) {
     const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
@@ -180,6 +182,18 @@ __global__ void __launch_bounds__(128) k_fused_raw(DirP d, QueryP q, ChunkP ch, 
     { int64_t t_last = t0 + (int64_t)(rows - 1) * dt; if (t_last > q.tmax) { if (q.tmax < t0) r_lo = rows; else r_hi = (uint32_t)((uint64_t)(q.tmax - t0) / dtu); } }
     if (r_lo > r_hi || r_lo >= rows) { if (lane == 0) { ch.edge_bucket[e] = OG_NO_BUCKET; ch.edge_bucket[e + 1] = OG_NO_BUCKET; } return; }
     const uint8_t *vals = d.data + d.page_off[(size_t)q.col_index[0] * d.n_segments + seg] + 6;
+    /* stage the page through shared memory with coalesced 16-byte loads (one DRAM round trip per page instead of one per
+     * row); pages longer than the staging buffer are read in place */
+    __shared__ __align__(16) uint8_t s_page[4][OG_RAW_STAGE];
+    const uint8_t *g16 = (const uint8_t *)((uintptr_t)vals & ~(uintptr_t)15);
+    const uint32_t mis = (uint32_t)(vals - g16), need = mis + 8 * rows;
+    const bool staged = need <= OG_RAW_STAGE;
+    if (staged) {
+        uint4 *dst = (uint4 *)s_page[threadIdx.x >> 5];
+        for (uint32_t o = lane; o * 16 < need; o += 32) dst[o] = __ldg((const uint4 *)g16 + o);
+        __syncwarp();
+    }
+    const uint8_t *srow = s_page[threadIdx.x >> 5] + mis;
     const uint32_t b_first = bucket_of(t0 + (int64_t)r_lo * dt, q.start, q.interval), b_last = bucket_of(t0 + (int64_t)r_hi * dt, q.start, q.interval);
     const uint32_t nwin = b_last - b_first + 1;
     for (uint32_t w = lane; w < nwin; w += 32) {
@@ -189,25 +203,39 @@ __global__ void __launch_bounds__(128) k_fused_raw(DirP d, QueryP q, ChunkP ch, 
         if (W0 > t0) { uint64_t k = ((uint64_t)(W0 - t0) + dtu - 1) / dtu; if (k > ra) ra = k > rb ? rb : (uint32_t)k; }
         { uint64_t k = ((uint64_t)(W1 - t0) + dtu - 1) / dtu; if (k < rb) rb = (uint32_t)k; }
         if (ra >= rb) continue; /* a window without rows (cadence coarser than the interval) */
-        Part parts[OG_MAX_CALLS];
-#pragma unroll
-        for (uint32_t c = 0; c < OG_MAX_CALLS; c++) parts[c] = part_empty();
+        /* same accumulators and seeding rules as k_fused_fast (first value seeds min/max/first; strict compares) */
+        double sum = 0.0; uint64_t mn = 0, mx = 0, fi = 0, lastv = 0; uint32_t r_mn = ra, r_mx = ra;
         for (uint32_t r = ra; r < rb; r++) {
-            const uint64_t v = ld_le64(vals + 8 * (size_t)r);
-            const int64_t t = t0 + (int64_t)r * dt;
-#pragma unroll
-            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) acc_row(q.calls[c].func, OG_TYPE_FLOAT, parts[c], v, t);
+            uint64_t v;
+            if (staged) { /* unaligned 8 bytes from three aligned words */
+                const uint8_t *pr = srow + 8 * (size_t)r;
+                const uint32_t *w32 = (const uint32_t *)((uintptr_t)pr & ~(uintptr_t)3);
+                const uint32_t sh = ((uint32_t)(uintptr_t)pr & 3) * 8;
+                v = ((uint64_t)__funnelshift_r(w32[1], w32[2], sh) << 32) | __funnelshift_r(w32[0], w32[1], sh);
+            }
+            else v = ld_le64(vals + 8 * (size_t)r);
+            if (r == ra) { mn = mx = fi = v; }
+            if (FM & FM_SUM) sum = sum + u2d(v);
+            if (FM & FM_MIN) { if (u2d(mn) > u2d(v)) { mn = v; r_mn = r; } }
+            if (FM & FM_MAX) { if (u2d(mx) < u2d(v)) { mx = v; r_mx = r; } }
+            lastv = v;
         }
-        if (w == 0) {
-#pragma unroll
-            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.edges[c], e, parts[c]);
-        } else if (w == nwin - 1) {
-#pragma unroll
-            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.edges[c], e + 1, parts[c]);
-        } else {
-            const size_t ci = cell_idx(ch, series, b_first + w);
-#pragma unroll
-            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) if (c < q.n_calls) store_part(ch.cells[c], ci, parts[c]);
+        const uint32_t cnt = rb - ra;
+        const int kind = w == 0 ? 0 : w == nwin - 1 ? 1 : 2;
+        const size_t idx = kind == 2 ? cell_idx(ch, series, b_first + w) : e + kind;
+#pragma unroll 1
+        for (uint32_t c = 0; c < q.n_calls; c++) {
+            Part pp; pp.ok = 1; pp.v = 0; pp.t = 0;
+            switch (q.calls[c].func) {
+            case OG_AGG_COUNT: pp.v = cnt; break;
+            case OG_AGG_SUM: pp.v = d2u(sum); break;
+            case OG_AGG_MIN: pp.v = mn; if (TIMES) pp.t = t0 + (int64_t)r_mn * dt; break;
+            case OG_AGG_MAX: pp.v = mx; if (TIMES) pp.t = t0 + (int64_t)r_mx * dt; break;
+            case OG_AGG_FIRST: pp.v = fi; pp.t = t0 + (int64_t)ra * dt; break;
+            default: pp.v = lastv; pp.t = t0 + (int64_t)(rb - 1) * dt; break;
+            }
+            const Tri &dst = kind == 2 ? ch.cells[c] : ch.edges[c];
+            store_part(dst, idx, pp);
         }
     }
     if (lane == 0) { ch.edge_bucket[e] = b_first; ch.edge_bucket[e + 1] = nwin > 1 ? b_last : OG_NO_BUCKET; }
