@@ -557,11 +557,16 @@ int build_plan(og_query *q) {
         pl->fm |= FM_COUNT; /* the row count also is the validity of every partial */
         q->path_used = 2;
     }
-    if (!pl->fused) { /* generic path: L2-sized materialisation tile */
+    if (!pl->fused) { /* generic path: materialisation tile */
         TileP &tp = pl->tp;
         tp.R = std::max<uint32_t>(1, s->max_seg_rows);
         size_t per_seg = (size_t)tp.R * (p.n_cols * 9 + 8 + 1);
-        q->tile_segs = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max<uint32_t>(1, max_chunk_segs), ((size_t)96 << 20) / per_seg));
+        /* the decode step is one thread per page: it needs hundreds of thousands of pages in flight to hide latency, so the
+         * tile is sized by free memory (a quarter of it, at most 12 GB), not by the L2 */
+        size_t fb = 0, tb = 0;
+        CU(cudaMemGetInfo(&fb, &tb));
+        const size_t tile_budget = std::max<size_t>((size_t)96 << 20, std::min<size_t>(fb / 4, (size_t)12 << 30));
+        q->tile_segs = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max<uint32_t>(1, max_chunk_segs), tile_budget / per_seg));
         for (uint32_t k = 0; k < p.n_cols; k++) {
             if ((rc = salloc(q, &tp.vals[k], (size_t)q->tile_segs * tp.R))) return rc;
             if ((rc = salloc(q, &tp.okb[k], (size_t)q->tile_segs * tp.R))) return rc;
