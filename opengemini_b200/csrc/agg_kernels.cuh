@@ -105,7 +105,10 @@ __global__ void k_fill_seg_series(const uint32_t *series_seg_begin, uint32_t n_s
  *   vals[slot][(seg-tile_begin)*R + row]  expanded to one cell per row, okb = validity byte per row
  * ------------------------------------------------------------------------------------------------------------ */
 struct TileP {
-    uint32_t tile_begin, tile_end, R; /* R = row stride per segment */
+    uint32_t tile_begin, tile_end, R; /* R = rows reserved per segment */
+    uint32_t S;                       /* segments per row of the tile (tile size rounded up to 32): cell (segment sl, row r)
+                                         lives at r*S + sl, so threads that own consecutive segments and walk their rows in
+                                         step read and write consecutive addresses */
     uint64_t *vals[OG_MAX_COLS];
     uint8_t *okb[OG_MAX_COLS];
     int64_t *times;
@@ -113,25 +116,25 @@ struct TileP {
 };
 
 struct ExpandEmit {
-    uint64_t *out; uint8_t *okb; const PageHdr *h; uint32_t row;
+    uint64_t *out; uint8_t *okb; const PageHdr *h; uint32_t row; size_t stride;
     __device__ __forceinline__ void operator()(uint32_t, uint64_t bits) {
-        while (row < h->rows && !hdr_row_valid(*h, row)) { out[row] = 0; okb[row] = 0; row++; }
-        if (row < h->rows) { out[row] = bits; okb[row] = 1; row++; }
+        while (row < h->rows && !hdr_row_valid(*h, row)) { out[row * stride] = 0; okb[row * stride] = 0; row++; }
+        if (row < h->rows) { out[row * stride] = bits; okb[row * stride] = 1; row++; }
     }
 };
-struct TimeStore { int64_t *out; __device__ __forceinline__ void operator()(uint32_t i, int64_t t) { out[i] = t; } };
+struct TimeStore { int64_t *out; size_t stride; __device__ __forceinline__ void operator()(uint32_t i, int64_t t) { out[i * stride] = t; } };
 
 __global__ void k_decode_tile(DirP d, QueryP q, TileP tp, int *err) {
     uint32_t seg = tp.tile_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= tp.tile_end) return;
     uint32_t slot = blockIdx.y;
-    size_t base = (size_t)(seg - tp.tile_begin) * tp.R;
+    const size_t base = seg - tp.tile_begin, S = tp.S;
     uint32_t rows = d.seg_rows[seg];
     if (slot == q.n_cols) {
         size_t ti = (size_t)d.n_columns * d.n_segments + seg;
         TimeDesc t;
         int rc = parse_time_page(d.data + d.page_off[ti], d.page_len[ti], t);
-        if (rc == D_OK) { TimeStore ts{tp.times + base}; rc = decode_time_values(t, ts); }
+        if (rc == D_OK) { TimeStore ts{tp.times + base, S}; rc = decode_time_values(t, ts); }
         if (rc != D_OK) report_err(err, rc, seg);
         return;
     }
@@ -139,13 +142,13 @@ __global__ void k_decode_tile(DirP d, QueryP q, TileP tp, int *err) {
     size_t pi = (size_t)col * d.n_segments + seg;
     uint64_t *out = tp.vals[slot] + base; uint8_t *okb = tp.okb[slot] + base;
     uint32_t len = d.page_len[pi];
-    if (len == 0) { for (uint32_t i = 0; i < rows; i++) { out[i] = 0; okb[i] = 0; } return; }
+    if (len == 0) { for (uint32_t i = 0; i < rows; i++) { out[i * S] = 0; okb[i * S] = 0; } return; }
     PageHdr h;
     int rc = parse_field_header(d.data + d.page_off[pi], len, type, rows, h);
     if (rc == D_OK) {
-        ExpandEmit em{out, okb, &h, 0};
+        ExpandEmit em{out, okb, &h, 0, S};
         rc = decode_block(type, h, em);
-        for (uint32_t i = em.row; i < rows; i++) { out[i] = 0; okb[i] = 0; }
+        for (uint32_t i = em.row; i < rows; i++) { out[i * S] = 0; okb[i * S] = 0; }
     }
     if (rc != D_OK) report_err(err, rc, seg);
 }
@@ -177,9 +180,10 @@ __device__ __forceinline__ bool term_pass(const FilterP &f, uint64_t raw) {
 
 __global__ void k_filter_tile(DirP d, QueryP q, TileP tp) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)(tp.tile_end - tp.tile_begin) * tp.R;
+    size_t total = (size_t)tp.S * tp.R;
     if (idx >= total) return;
-    uint32_t sl = (uint32_t)(idx / tp.R), row = (uint32_t)(idx % tp.R);
+    uint32_t row = (uint32_t)(idx / tp.S), sl = (uint32_t)(idx % tp.S);
+    if (sl >= tp.tile_end - tp.tile_begin) return;
     if (row >= d.seg_rows[tp.tile_begin + sl]) { tp.keep[idx] = 0; return; }
     int64_t t = tp.times[idx];
     bool keep = t >= q.tmin && t <= q.tmax;
@@ -209,41 +213,51 @@ __device__ __forceinline__ void emit_window(const QueryP &q, const ChunkP &ch, u
     else if (p.ok) store_part(ch.cells[call], cell_idx(ch, series, b), p);
 }
 
-/* step 3: one warp per segment, one lane per window of that segment; rows of a window are walked in order so
- * float sums keep the reference's left-to-right order (series_agg_func.gen.go:48-60). */
+/* step 3: one thread per segment walks its rows in time order (threads of a warp own consecutive segments and move row by row
+ * together, so every load is coalesced in the r*S + sl layout); the rows of a window are accumulated left to right, which keeps
+ * float sums in the reference's order (series_agg_func.gen.go:48-60).  Windows are those of the rows inside [tmin, tmax]; rows
+ * removed by the WHERE mask do not contribute, a window whose rows were all removed yields an invalid partial. */
 __global__ void k_window_reduce(DirP d, QueryP q, TileP tp, ChunkP ch) {
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    uint32_t seg = tp.tile_begin + warp;
+    uint32_t sl = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t seg = tp.tile_begin + sl;
     if (seg >= tp.tile_end) return;
-    uint32_t rows = d.seg_rows[seg], series = d.seg_series[seg];
-    size_t base = (size_t)(seg - tp.tile_begin) * tp.R;
-    const int64_t *tm = tp.times + base;
-    const uint8_t *keep = tp.keep + base;
-    size_t e = 2 * (size_t)(seg - ch.seg_begin);
-    int64_t lo = rows ? tm[0] : 1, hi = rows ? tm[rows - 1] : 0;
-    if (lo < q.tmin) lo = q.tmin;
-    if (hi > q.tmax) hi = q.tmax;
-    if (lo > hi) { if (lane == 0) { ch.edge_bucket[e] = OG_NO_BUCKET; ch.edge_bucket[e + 1] = OG_NO_BUCKET; } return; }
-    uint32_t b0 = bucket_of(lo, q.start, q.interval), b1 = bucket_of(hi, q.start, q.interval);
-    uint32_t nwin = b1 - b0 + 1;
-    if (lane == 0) { ch.edge_bucket[e] = b0; ch.edge_bucket[e + 1] = nwin > 1 ? b1 : OG_NO_BUCKET; }
-    for (uint32_t w = lane; w < nwin; w += 32) {
-        uint32_t b = b0 + w;
-        int64_t ws = q.start + (int64_t)b * q.interval, we = ws + q.interval;
-        /* lower_bound(t >= ws), lower_bound(t >= we) over the sorted time column */
-        uint32_t r0 = 0, r1 = rows;
-        { uint32_t a = 0, z = rows; while (a < z) { uint32_t m = (a + z) >> 1; if (tm[m] < ws) a = m + 1; else z = m; } r0 = a; }
-        { uint32_t a = r0, z = rows; while (a < z) { uint32_t m = (a + z) >> 1; if (tm[m] < we) a = m + 1; else z = m; } r1 = a; }
+    const uint32_t rows = d.seg_rows[seg], series = d.seg_series[seg];
+    const size_t S = tp.S, e = 2 * (size_t)(seg - ch.seg_begin);
+    Part parts[OG_MAX_CALLS];
+    uint32_t cur_b = OG_NO_BUCKET, head_b = OG_NO_BUCKET; bool head_done = false;
+    int64_t we = 0;
+    auto flush = [&](bool final) {
+        if (cur_b == OG_NO_BUCKET) return;
         for (uint32_t c = 0; c < q.n_calls; c++) {
+            if (!head_done) store_part(ch.edges[c], e, parts[c]);
+            else if (final) store_part(ch.edges[c], e + 1, parts[c]);
+            else if (parts[c].ok) store_part(ch.cells[c], cell_idx(ch, series, cur_b), parts[c]);
+        }
+        if (!head_done) { head_done = true; head_b = cur_b; }
+    };
+    for (uint32_t r = 0; r < rows; r++) {
+        const size_t ix = (size_t)r * S + sl;
+        const int64_t t = tp.times[ix];
+        if (t < q.tmin) continue;
+        if (t > q.tmax) break;
+        if (cur_b == OG_NO_BUCKET || t >= we) {
+            flush(false);
+            cur_b = bucket_of(t, q.start, q.interval);
+            we = q.start + (int64_t)(cur_b + 1) * q.interval;
+#pragma unroll
+            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) parts[c] = part_empty();
+        }
+        if (!tp.keep[ix]) continue;
+#pragma unroll
+        for (uint32_t c = 0; c < OG_MAX_CALLS; c++) {
+            if (c >= q.n_calls) break;
             const CallP &cp = q.calls[c];
-            const uint64_t *vals = tp.vals[cp.col_slot] + base;
-            const uint8_t *okb = tp.okb[cp.col_slot] + base;
-            Part p = part_empty();
-            for (uint32_t r = r0; r < r1; r++)
-                if (keep[r] && okb[r]) acc_row(cp.func, cp.type, p, vals[r], tm[r]);
-            emit_window(q, ch, seg, series, b, w == 0, nwin > 1 && w == nwin - 1, (int)c, p);
+            if (tp.okb[cp.col_slot][ix]) acc_row(cp.func, cp.type, parts[c], tp.vals[cp.col_slot][ix], t);
         }
     }
+    flush(true);
+    ch.edge_bucket[e] = head_b;
+    ch.edge_bucket[e + 1] = (head_b == OG_NO_BUCKET || cur_b == head_b) ? OG_NO_BUCKET : cur_b;
 }
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -567,6 +567,8 @@ int build_plan(og_query *q) {
         CU(cudaMemGetInfo(&fb, &tb));
         const size_t tile_budget = std::max<size_t>((size_t)96 << 20, std::min<size_t>(fb / 4, (size_t)12 << 30));
         q->tile_segs = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max<uint32_t>(1, max_chunk_segs), tile_budget / per_seg));
+        q->tile_segs = std::max<uint32_t>(32, q->tile_segs & ~31u);
+        tp.S = q->tile_segs;
         for (uint32_t k = 0; k < p.n_cols; k++) {
             if ((rc = salloc(q, &tp.vals[k], (size_t)q->tile_segs * tp.R))) return rc;
             if ((rc = salloc(q, &tp.okb[k], (size_t)q->tile_segs * tp.R))) return rc;
@@ -650,9 +652,9 @@ OG_API int og_query_run(og_query *q) {
                 uint32_t n = tp.tile_end - tp.tile_begin;
                 dim3 g((n + 127) / 128, p.n_cols + 1);
                 k_decode_tile<<<g, 128, 0, st>>>(dir, p, tp, q->d_err);
-                size_t rows_total = (size_t)n * tp.R;
+                size_t rows_total = (size_t)tp.S * tp.R;
                 k_filter_tile<<<(unsigned)((rows_total + 255) / 256), 256, 0, st>>>(dir, p, tp);
-                k_window_reduce<<<(n * 32 + 127) / 128, 128, 0, st>>>(dir, p, tp, ch);
+                k_window_reduce<<<(n + 127) / 128, 128, 0, st>>>(dir, p, tp, ch);
                 launches += 3;
             }
         }
@@ -832,7 +834,7 @@ __global__ void k_decode_column(DirP d, uint32_t column, int type, uint32_t seg_
     if (column == d.n_columns) { /* time column */
         TimeDesc t;
         int rc = parse_time_page(d.data + d.page_off[pi], d.page_len[pi], t);
-        if (rc == D_OK) { TimeStore ts{(int64_t *)o}; rc = decode_time_values(t, ts); }
+        if (rc == D_OK) { TimeStore ts{(int64_t *)o, 1}; rc = decode_time_values(t, ts); }
         if (rc != D_OK) report_err(err, rc, seg);
         if (rows_out) rows_out[seg - seg_begin] = rows;
         return;
