@@ -497,6 +497,10 @@ int build_plan(og_query *q) {
     CU(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
     q->chunk_series = (uint32_t)std::max<size_t>(1, std::min<size_t>(s->n_series, budget / std::max<size_t>(1, cell_bytes_per_series)));
+    if (const char *ov = getenv("OGPU_CHUNK_SERIES")) { /* test hook: force small chunks so the multi-chunk paths get exercised */
+        long v = atol(ov);
+        if (v > 0) q->chunk_series = (uint32_t)std::min<long>(v, (long)std::max<uint32_t>(1, s->n_series));
+    }
     if (q->chunk_series < s->n_series) q->chunk_series = std::max<uint32_t>(32, q->chunk_series & ~31u); /* lane groups of 32 series never straddle chunks */
     uint32_t max_chunk_segs = 0;
     for (uint32_t a = 0; a < s->n_series; a += q->chunk_series) {

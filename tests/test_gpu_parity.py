@@ -440,3 +440,56 @@ def test_encode_pages_roundtrip_on_device():
         want = oracle.field_page_encode(L.TYPE_FLOAT, vals[g * rps:(g + 1) * rps])
         got = pages[offs[g]:offs[g] + lens[g]]
         assert np.array_equal(got, want), f"segment {g}"
+
+
+def _ragged_shard(seg_counts, n=500):
+    """Series with different numbers of segments (so lane groups are 32 consecutive segments, not 32 series)."""
+    rng = np.random.default_rng(12)
+    pages, tpages, tmins, tmaxs, ssb = [], [], [], [], [0]
+    for k in seg_counts:
+        for g in range(k):
+            v = 100.0 + rng.random(n)
+            if g == 1:
+                v = rng.integers(0, 2**62, n).astype(np.uint64).view(np.float64)  # incompressible -> raw page
+                v = np.where(np.isfinite(v), v, 1.0)
+            pages.append(oracle.field_page_encode(L.TYPE_FLOAT, v))
+            t = T0 + (np.arange(n, dtype=np.int64) + g * n) * SEC
+            tpages.append(oracle.time_page_encode(t)); tmins.append(t[0]); tmaxs.append(t[-1])
+        ssb.append(ssb[-1] + k)
+    blob, offs, lens, pos = [], [], [], 0
+    for p in pages + tpages:
+        offs.append(pos); lens.append(p.size); blob.append(p); pos += p.size
+    nseg = ssb[-1]
+    sh = Shard.open(np.concatenate(blob), np.arange(1, len(seg_counts) + 1), ssb, tmins, tmaxs,
+                    [("v", L.TYPE_FLOAT, offs[:nseg], lens[:nseg])], offs[nseg:], lens[nseg:])
+    return sh, oracle.shard_desc_from_export(sh.export()), T0 + max(seg_counts) * n * SEC
+
+
+@pytest.mark.gpu
+def test_ragged_series_use_consecutive_segment_groups():
+    sh, sd, tmax = _ragged_shard([1, 2, 3, 5, 8, 13, 2, 1, 40])
+    for calls in ([("sum", 0), ("count", 0), ("max", 0)], [("min", 0)], [("first", 0), ("last", 0)]):
+        for group in ("all", "series"):
+            run_both(sh, sd, calls, 60 * SEC, T0, tmax, f"ragged {calls} {group}", group=group)
+    run_both(sh, sd, [("sum", 0), ("max", 0)], 45 * SEC, T0 + 123 * SEC, T0 + 2345 * SEC, "ragged mid-range")
+    sh.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", ["32", "7"])
+def test_multi_chunk_plans(monkeypatch, chunk):
+    """OGPU_CHUNK_SERIES forces several chunks of series per query (as happens when the cell matrix outgrows memory)."""
+    monkeypatch.setenv("OGPU_CHUNK_SERIES", chunk)
+    cols = [(L.TYPE_FLOAT, L.SYNTH_F_HI, 0), (L.TYPE_INT, L.SYNTH_INT_WALK, 30)]
+    sh = Shard.synth(100, 3000, cols, t0=T0, dt=SEC, seed=5)
+    hs = oracle.HostShard(100, 3000, cols, t0=T0, dt=SEC, seed=5)
+    tmax = T0 + 2999 * SEC
+    run_both(sh, hs.desc, [("sum", 0), ("count", 0), ("max", 0)], 60 * SEC, T0, tmax, "chunks fast")
+    run_both(sh, hs.desc, [("min", 0)], 300 * SEC, T0, tmax, "chunks fast selector", group="series")
+    run_both(sh, hs.desc, [("sum", 1), ("last", 1)], 60 * SEC, T0, tmax, "chunks general int")
+    run_both(sh, hs.desc, [("count", 1), ("sum", 0)], 60 * SEC, T0, tmax, "chunks tile", filter=[("term", 0, ">", 100.5)])
+    run_both(sh, hs.desc, [("max", 0), ("count", 1)], 120 * SEC, T0, tmax, "chunks map", group="map", series_group=np.arange(100) % 3, n_groups=3)
+    sh.close()
+    ragged, sd, tm = _ragged_shard([3, 1, 4, 1, 5, 9, 2, 6])
+    run_both(ragged, sd, [("sum", 0), ("count", 0), ("max", 0)], 60 * SEC, T0, tm, "chunks ragged")
+    ragged.close()
