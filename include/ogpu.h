@@ -86,14 +86,15 @@ typedef struct og_call {
 
 enum { OG_GROUP_ALL = 0, OG_GROUP_PER_SERIES = 1, OG_GROUP_MAP = 2 };
 enum {
-    OG_Q_STRICT_ORDER = 1u << 0 /* cross-series float sums in strict series order (bit-exact with the reference's
-                                   sequential merge, lib/record/reccord_functions.go:730-733) instead of chunked order */
+    OG_Q_STRICT_ORDER = 1u << 0 /* cross-series float sums in strict series order (bit-exact with the reference's sequential
+                                   merge, lib/record/reccord_functions.go:730-733).  Every path of this version already folds
+                                   in that order, so the flag changes nothing today; it pins the behaviour for callers. */
     ,
     OG_Q_NO_FUSED = 1u << 1 /* force the generic materialise-tile path even when the fused kernel is eligible (testing / A-B) */
     ,
     OG_Q_NO_FAST = 1u << 2 /* fused path, but without the specialised Gorilla/const-delta kernel (testing / A-B) */
     ,
-    OG_Q_STAGE_TMA = 1u << 3 /* fast kernel: stage pages with per-lane cp.async.bulk copies instead of warp-cooperative loads (A-B) */
+    OG_Q_RESERVED_8 = 1u << 3 /* was an A/B switch of the round-1 staging experiments; ignored */
 };
 
 typedef struct og_query_desc {
@@ -122,7 +123,7 @@ typedef struct og_column_desc {
 
 enum {
     OG_SHARD_DEVICE_DATA = 1u << 0 /* `data` is a device pointer owned by the caller for the shard's lifetime (zero-copy);
-                                      the allocation must extend >= 1024 readable bytes past data_len (whole-chunk TMA copies) */
+                                      the allocation must extend >= 1024 readable bytes past data_len (word-granular over-reads of the last page) */
 };
 
 typedef struct og_shard_desc {

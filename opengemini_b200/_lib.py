@@ -20,7 +20,6 @@ GROUP_ALL, GROUP_PER_SERIES, GROUP_MAP = 0, 1, 2
 Q_STRICT_ORDER = 1
 Q_NO_FUSED = 2
 Q_NO_FAST = 4
-Q_STAGE_TMA = 8
 SYNTH_F_HI, SYNTH_F_LO, SYNTH_INT_WALK, SYNTH_BOOL = 0, 1, 2, 3
 SHARD_DEVICE_DATA = 1
 

@@ -179,7 +179,7 @@ OG_API int og_shard_open(const og_shard_desc *d, og_shard **out) {
 #define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = cuda_fail(e_, #x, __FILE__, __LINE__); og_shard_close(s); return rc; } } while (0)
     if (d->flags & OG_SHARD_DEVICE_DATA) { s->d_data = (uint8_t *)d->data; s->owns_data = false; }
     else {
-        TRY(dalloc(&s->d_data, d->data_len + 1024)); /* tail padding: word-wise unaligned loads and whole-chunk TMA copies read past the last page */
+        TRY(dalloc(&s->d_data, d->data_len + 1024)); /* tail padding: word-wise unaligned loads and the interleave repack read past the last page */
         TRYCU(cudaMemcpy(s->d_data, d->data, d->data_len, cudaMemcpyHostToDevice));
         TRYCU(cudaMemset(s->d_data + d->data_len, 0, 1024));
     }
