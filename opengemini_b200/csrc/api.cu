@@ -52,6 +52,7 @@ static DirP make_dir(const og_shard *s) {
 /* derive seg_series / seg_rows / totals and validate codecs; shared by og_shard_open and og_shard_synth */
 int shard_finalize(og_shard *s) {
     int rc;
+    s->il.resize(s->n_columns); /* sized once here: queries only read/lock individual entries later */
     if ((rc = dalloc(&s->d_seg_series, s->n_segments))) return rc;
     if ((rc = dalloc(&s->d_seg_rows, s->n_segments))) return rc;
     int32_t *d_types; unsigned long long *d_tot; uint32_t *d_max; int *d_err;
@@ -402,6 +403,7 @@ void launch_fast(int fm, bool times, const FastArgs &stage, const DirP &d, const
 /* Build (once per shard and column) the lane-interleaved stream copy that k_fused_fast reads.  Returns OG_OK with
  * state 1 (ready) or -1 (nothing eligible / not enough memory: the general fused kernel serves the column instead). */
 int ensure_il(og_shard *s, int col, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(s->il_mu);
     if (s->il.size() != s->n_columns) s->il.resize(s->n_columns);
     og_shard::IlCol &ic = s->il[col];
     if (ic.state != 0) return OG_OK;

@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/ogpu.h"
@@ -55,6 +56,7 @@ struct og_shard {
                    uint32_t *lane_seg = nullptr; uint32_t n_groups = 0, segs_per_series = 0; /* segs_per_series != 0: lanes = 32 consecutive series */
                    uint64_t n_words = 0; double build_ms = 0; };
     std::vector<IlCol> il; /* [n_columns] */
+    std::mutex il_mu;      /* queries of one shard may be planned from different threads: the build is serialised */
 };
 
 namespace ogpu {
