@@ -393,6 +393,37 @@ __global__ void __launch_bounds__(128) k_merge_all(QueryP q, ChunkP ch, GroupP g
     if (b0 + t < nb) store_part(gp.dense[c], b0 + t, acc);
 }
 
+/* OG_GROUP_PER_SERIES: every tagset is one series, so the merge is a transposition of the bucket-major cell matrix into the
+ * series-major dense record — done through a 32x32 shared-memory tile so both sides are coalesced.  Each element still goes
+ * through group_update on an empty accumulator (same value/time rules as the general merge); k_init_dense is not needed. */
+__global__ void __launch_bounds__(256) k_merge_per_series(QueryP q, ChunkP ch, GroupP gp) {
+    __shared__ uint64_t sv[32][33];
+    __shared__ int64_t st[32][33];
+    __shared__ uint8_t sk[32][36];
+    const uint32_t c = blockIdx.z, b0 = blockIdx.x * 32, s0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
+    const uint32_t nS = ch.series_end - ch.series_begin, nb = q.n_buckets;
+    const CallP &cp = q.calls[c];
+    const int ftype = cp.out_type == OG_TYPE_INT && cp.func == OG_AGG_COUNT ? OG_TYPE_INT : cp.type;
+    const Tri cells = ch.cells[c];
+    for (uint32_t j = ty; j < 32; j += 8) {
+        const uint32_t b = b0 + j, sr = s0 + tx;
+        const bool in = b < nb && sr < nS;
+        const size_t ci = in ? (size_t)b * ch.cell_sb + sr : 0;
+        sk[j][tx] = in ? cells.ok[ci] : (uint8_t)0;
+        sv[j][tx] = in ? cells.val[ci] : 0;
+        st[j][tx] = (in && cells.tim) ? cells.tim[ci] : 0;
+    }
+    __syncthreads();
+    for (uint32_t j = ty; j < 32; j += 8) {
+        const uint32_t sr = s0 + j, b = b0 + tx;
+        if (sr >= nS || b >= nb) continue;
+        Part p; p.ok = sk[tx][j]; p.v = sv[tx][j]; p.t = st[tx][j];
+        Part a; a.v = 0; a.ok = 0; a.t = q.multi ? 0 : q.start + (int64_t)b * q.interval;
+        group_update(cp.func, ftype, q.multi != 0, a, p);
+        store_part(gp.dense[c], (size_t)(ch.series_begin + sr) * nb + b, a);
+    }
+}
+
 /* dense initialisation: values 0, valid 0, times = window start (single-call selectors) or 0 (RecMeta.Times) */
 __global__ void k_init_dense(QueryP q, GroupP gp) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -608,7 +608,8 @@ OG_API int og_query_run(og_query *q) {
     while (q->main_ev.size() < 2 * (size_t)n_chunks) { cudaEvent_t e; CU(cudaEventCreate(&e)); q->main_ev.push_back(e); }
     CU(cudaMemsetAsync(q->d_err, 0, 8, st));
     CU(cudaEventRecord(q->ev0, st));
-    k_init_dense<<<(unsigned)((cells_dense + 255) / 256), 256, 0, st>>>(p, gp); launches++;
+    const bool per_series = q->desc.group_mode == OG_GROUP_PER_SERIES;
+    if (!per_series) { k_init_dense<<<(unsigned)((cells_dense + 255) / 256), 256, 0, st>>>(p, gp); launches++; } /* per-series: k_merge_per_series writes every cell */
     uint64_t segs_scanned = 0; uint32_t ci = 0, chunks_run = 0;
     for (uint32_t a = 0; a < s->n_series; a += q->chunk_series, ci++) {
         if (q->aborted) { cudaStreamSynchronize(st); set_error("query aborted"); return OG_E_ABORTED; }
@@ -616,7 +617,14 @@ OG_API int og_query_run(og_query *q) {
         ch.series_begin = a; ch.series_end = b;
         ch.seg_begin = s->h_series_seg_begin[a]; ch.seg_end = s->h_series_seg_begin[b];
         uint32_t nseg = ch.seg_end - ch.seg_begin;
-        if (nseg == 0) continue;
+        if (nseg == 0) {
+            if (per_series) { /* series without segments still own dense rows: write them as empty */
+                for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)ch.cell_sb * p.n_buckets, st));
+                k_merge_per_series<<<dim3((p.n_buckets + 31) / 32, (b - a + 31) / 32, p.n_calls), dim3(32, 8), 0, st>>>(p, ch, gp);
+                launches++;
+            }
+            continue;
+        }
         segs_scanned += nseg;
         for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)ch.cell_sb * p.n_buckets, st));
         CU(cudaEventRecord(q->main_ev[2 * chunks_run], st));
@@ -669,7 +677,8 @@ OG_API int og_query_run(og_query *q) {
         k_fix_edges<<<(nseg + 127) / 128, 128, 0, st>>>(dir, p, ch);
         bool any_tim = false;
         for (uint32_t c = 0; c < p.n_calls; c++) any_tim |= gp.dense[c].tim != nullptr;
-        if (q->desc.group_mode == OG_GROUP_ALL && !any_tim) k_merge_all<<<dim3((p.n_buckets + 127) / 128, p.n_calls), 128, 0, st>>>(p, ch, gp);
+        if (per_series) k_merge_per_series<<<dim3((p.n_buckets + 31) / 32, (b - a + 31) / 32, p.n_calls), dim3(32, 8), 0, st>>>(p, ch, gp);
+        else if (q->desc.group_mode == OG_GROUP_ALL && !any_tim) k_merge_all<<<dim3((p.n_buckets + 127) / 128, p.n_calls), 128, 0, st>>>(p, ch, gp);
         else k_merge_groups<<<dim3((unsigned)((cells_dense + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp);
         launches += 2;
     }
