@@ -6,6 +6,13 @@ import numpy as np, torch
 from opengemini_b200 import AggQuery, Shard, _lib as L
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 T0, SEC, rows = 1_700_000_000_000_000_000, 1_000_000_000, 1_000_000
+if len(sys.argv) > 2 and sys.argv[2] == "affinity":
+    import pynvml
+    pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    print("cpu affinity before", len(os.sched_getaffinity(0)))
+    pynvml.nvmlDeviceSetCpuAffinity(h)
+    print("cpu affinity after nvmlDeviceSetCpuAffinity", sorted(os.sched_getaffinity(0))[:4], "...", len(os.sched_getaffinity(0)))
+os.system("nvidia-smi topo -m 2>/dev/null | head -4; numactl -H 2>/dev/null | head -3")
 Shard.init(0)
 small = Shard.synth(ns, rows, [(L.TYPE_FLOAT, L.SYNTH_F_HI, 0)], t0=T0, dt=SEC, seed=1000)
 ex = small.export()
