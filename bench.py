@@ -336,19 +336,30 @@ def run_ours(a):
         h2d = int(lay.data_len + lay.n_segments * (2 * 12 + 16) + ns * 12)
         e_steps = max(1, min(a.steps, 3))
 
+        phases = {"open": 0.0, "query": 0.0, "records": 0.0, "close": 0.0}
+
         def e2e_step():
+            p0 = time.perf_counter()
             s2 = Shard.open(host_data, ex["sids"], ex["series_seg_begin"], ex["seg_tmin"], ex["seg_tmax"],
                             [("f0", L.TYPE_FLOAT, ex["page_off"][0], ex["page_len"][0])], ex["page_off"][1], ex["page_len"][1])
+            p1 = time.perf_counter()
             q2 = AggQuery(s2, calls, 60 * SEC, T0, tmax).run()
+            p2 = time.perf_counter()
             out_rows, d2h = 0, 0
             for rec in q2.records():
                 out_rows += rec["rows"]
                 d2h += sum(c["values"].nbytes + (c["len"] + 7) // 8 for c in rec["cols"]) + rec["times"].nbytes
             ln = q2.stats()["kernel_launches"] + 2
+            p3 = time.perf_counter()
             q2.close(); s2.close()
+            p4 = time.perf_counter()
+            for k, v in zip(("open", "query", "records", "close"), (p1 - p0, p2 - p1, p3 - p2, p4 - p3)):
+                phases[k] += v * 1e3
             return out_rows, d2h, ln
 
         e2e_step()
+        for k in phases:
+            phases[k] = 0.0
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -365,7 +376,7 @@ def run_ours(a):
         d2h_full = 16667 * 3 * 9
         e2e = {"value": e_rows * e_steps / et.item(), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": max(d2h, d2h_full),
                "sample": f"{ns} series x {a.rows} rows per GPU per step (host-resident, pinned), og_shard_open + og_query_run + og_query_next",
-               "steps": e_steps, "ms_per_step": et.item() / e_steps * 1e3, "out_rows": out_rows}
+               "steps": e_steps, "phase_ms_per_step": {k: round(v / e_steps, 2) for k, v in phases.items()}, "ms_per_step": et.item() / e_steps * 1e3, "out_rows": out_rows}
         del pinned
 
     cpu = None
