@@ -426,19 +426,20 @@ int ensure_il(og_shard *s, int col, cudaStream_t st) {
     ic.n_groups = ng; ic.segs_per_series = J;
     uint32_t *seg_words = nullptr;
     int rc;
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    struct Ev { cudaEvent_t e = nullptr; Ev() { cudaEventCreate(&e); } ~Ev() { if (e) cudaEventDestroy(e); } } ev0, ev1; /* destroyed on every return path */
+    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     cudaEventRecord(e0, st);
     if ((rc = dalloc(&ic.ok, (size_t)s->n_segments))) return rc;
     if ((rc = dalloc(&seg_words, (size_t)s->n_segments))) return rc;
-    if ((rc = dalloc(&ic.grp_words, (size_t)ng))) { cudaFree(seg_words); return rc; }
-    if ((rc = dalloc(&ic.grp_off, (size_t)ng))) { cudaFree(seg_words); return rc; }
+    struct Free { void *p; ~Free() { cudaFree(p); } } free_seg_words{seg_words};
+    if ((rc = dalloc(&ic.grp_words, (size_t)ng))) return rc;
+    if ((rc = dalloc(&ic.grp_off, (size_t)ng))) return rc;
     DirP d = make_dir(s);
     k_il_scan<<<(s->n_segments + 255) / 256, 256, 0, st>>>(d, col, s->col_types[col], ic.ok, seg_words);
     k_il_group_words<<<(unsigned)(((size_t)ng * 32 + 255) / 256), 256, 0, st>>>(ng, ic.lane_seg, seg_words, ic.grp_words);
     std::vector<uint32_t> gw(ng); std::vector<uint64_t> go(ng);
     CU(cudaMemcpyAsync(gw.data(), ic.grp_words, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(seg_words);
     uint64_t total = 0;
     for (uint32_t g = 0; g < ng; g++) { go[g] = total; total += (uint64_t)gw[g] * 32; }
     if (total == 0) return OG_OK;
@@ -451,7 +452,7 @@ int ensure_il(og_shard *s, int col, cudaStream_t st) {
     CU(cudaGetLastError());
     cudaEventRecord(e1, st);
     CU(cudaStreamSynchronize(st));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     ic.n_words = total; ic.build_ms = ms; ic.state = 1;
     return OG_OK;
 }

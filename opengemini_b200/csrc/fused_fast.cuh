@@ -48,6 +48,9 @@ enum { FM_COUNT = 1, FM_SUM = 2, FM_MIN = 4, FM_MAX = 8, FM_FIRST = 16, FM_LAST 
 enum { SEG_GENERAL = 0, SEG_FAST = 1, SEG_RAW = 2 };  /* per-segment classes computed by k_classify */
 
 #define OG_FAST_THREADS 128
+#ifndef OG_FAST_MINB
+#define OG_FAST_MINB 1
+#endif
 #ifndef OG_IL_NW
 #define OG_IL_NW 32u            /* window rows (words per lane) */
 #endif
@@ -250,7 +253,7 @@ __device__ __forceinline__ uint64_t fetch64(uint32_t col, uint32_t p) {
 }
 
 template <int FM, bool TIMES>
-__global__ void __launch_bounds__(OG_FAST_THREADS) k_fused_fast(DirP d, QueryP q, ChunkP ch, const uint8_t *cls, IlP il, uint32_t grp_begin, uint32_t grp_end) {
+__global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_fast(DirP d, QueryP q, ChunkP ch, const uint8_t *cls, IlP il, uint32_t grp_begin, uint32_t grp_end) {
     constexpr uint32_t NW = OG_IL_NW;
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ __align__(128) uint32_t s_win[(OG_FAST_THREADS / 32) * OG_IL_ROWS * 32];
