@@ -259,6 +259,7 @@ OG_API void og_query_destroy(og_query *q) {
     cudaFree(q->d_group_of_series);
     if (q->ev0) cudaEventDestroy(q->ev0);
     if (q->ev1) cudaEventDestroy(q->ev1);
+    for (cudaEvent_t e : q->main_ev) cudaEventDestroy(e);
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
 }

@@ -46,7 +46,7 @@ struct Error {
     const char *Error_() const { return msg.c_str(); }
 };
 
-/* record.ColVal (column.go:30-37).  Views into library-owned pinned memory. */
+/* record.ColVal (column.go:30-37).  Views into library-owned host memory. */
 struct ColVal {
     const uint8_t *Val = nullptr; size_t ValBytes = 0;
     const uint8_t *Bitmap = nullptr;
