@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_fast(Di
     }
 
     /* ---- per-window partials ---- */
-    double sum = 0.0; uint64_t mn = 0, mx = 0, fi = 0, lastv = 0;
+    double sum = 0.0, mn = 0.0, mx = 0.0; uint64_t fi = 0, lastv = 0; /* min/max live as doubles: aligned register pairs for DSETP */
     uint32_t n_mn = 0, n_mx = 0;  /* countdown value at the extreme row (row = stop - countdown) */
     uint32_t w_row0 = r_lo;       /* first row of the open window */
     bool head_done = false; uint32_t head_b = OG_NO_BUCKET;
@@ -328,8 +328,8 @@ __global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_fast(Di
         switch (func) {
         case OG_AGG_COUNT: pp.v = cnt; break;
         case OG_AGG_SUM: if (FM & FM_SUM) pp.v = d2u(sum); break;
-        case OG_AGG_MIN: if (FM & FM_MIN) { pp.v = mn; if (TIMES) pp.t = t0 + (int64_t)(stop - n_mn) * dt; } break;
-        case OG_AGG_MAX: if (FM & FM_MAX) { pp.v = mx; if (TIMES) pp.t = t0 + (int64_t)(stop - n_mx) * dt; } break;
+        case OG_AGG_MIN: if (FM & FM_MIN) { pp.v = d2u(mn); if (TIMES) pp.t = t0 + (int64_t)(stop - n_mn) * dt; } break;
+        case OG_AGG_MAX: if (FM & FM_MAX) { pp.v = d2u(mx); if (TIMES) pp.t = t0 + (int64_t)(stop - n_mx) * dt; } break;
         case OG_AGG_FIRST: if (FM & FM_FIRST) { pp.v = fi; pp.t = t0 + (int64_t)w_row0 * dt; } break;
         default: if (FM & FM_LAST) { pp.v = lastv; pp.t = t0 + (int64_t)(stop - 1) * dt; } break;
         }
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_fast(Di
     bool skipping = r_lo > 0;
     uint32_t stop = skipping ? r_lo : (rb < r_hi + 1 ? rb : r_hi + 1); /* row index of the next event */
     uint32_t n_ev = stop; /* rows until the next event (row 0 is current) */
-    if (!skipping) { mn = mx = fi = val; n_mn = n_mx = n_ev; }
+    if (!skipping) { fi = val; mn = mx = u2d(val); n_mn = n_mx = n_ev; }
 
     /* Refill schedule.  Service s (every K records) copies 8-word batches up to (p_s>>5) + NW (so at least up to
      * (p_s>>5) + NW - 7) and then waits for the PREVIOUS service's group.  Until service s+1 the lane reads at most
@@ -392,14 +392,14 @@ __global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_fast(Di
             w_row0 = stop;
             uint32_t nstop = rb < r_hi + 1 ? rb : r_hi + 1;
             n_ev = nstop - stop; stop = nstop;
-            mn = mx = fi = val; n_mn = n_mx = n_ev; /* the first value of a window seeds min/max/first (column_util.go:190-278) */
+            fi = val; mn = mx = u2d(val); n_mn = n_mx = n_ev; /* the first value of a window seeds min/max/first (column_util.go:190-278) */
         }
     };
     auto record = [&]() {
         /* accumulate the current row */
         if (FM & FM_SUM) sum = sum + u2d(val);
-        if (FM & FM_MIN) { if (u2d(mn) > u2d(val)) { mn = val; if (TIMES) n_mn = n_ev; } }
-        if (FM & FM_MAX) { if (u2d(mx) < u2d(val)) { mx = val; if (TIMES) n_mx = n_ev; } }
+        if (FM & FM_MIN) { if (mn > u2d(val)) { mn = u2d(val); if (TIMES) n_mn = n_ev; } }
+        if (FM & FM_MAX) { if (mx < u2d(val)) { mx = u2d(val); if (TIMES) n_mx = n_ev; } }
         if (FM & FM_LAST) lastv = val;
         n_ev--;
         /* next record (batch_float.go:352-508) */
