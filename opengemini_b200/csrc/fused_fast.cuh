@@ -1,6 +1,8 @@
 /*
  * fused_fast.cuh — K5 specialised for the headline shape: float64 Gorilla pages (tag 3, no nulls) with const-delta
- * time pages.  One thread per segment, a warp = 32 consecutive segments ("lane group").
+ * time pages.  One thread per segment; a warp = one "lane group" of 32 segments: segment j of 32 CONSECUTIVE SERIES on
+ * regular shards (every series has the same number of segments), so that the lanes share window boundaries, flush together and
+ * write one bucket of 32 series as one 256-byte run; otherwise 32 consecutive segments.
  *
  *   layout    Gorilla decode is serial per stream, so a warp reads 32 different pages.  To make those reads coalesced
  *             the shard keeps, next to the pages, a LANE-INTERLEAVED copy of every eligible stream (built once per
@@ -9,17 +11,20 @@
  *             holds word w of all 32 lanes: a warp-wide 4-byte access is one fully used line, in HBM and in shared
  *             memory alike, whatever the lanes' individual positions are.
  *   staging   each lane copies ITS words with 4-byte cp.async (LDGSTS) into the warp's shared-memory window
- *             [64 rows + 2 mirror rows][32 lanes]; bank = lane, so neither the copies nor the loads ever conflict.
+ *             [OG_IL_NW rows + 2 mirror rows][32 lanes]; bank = lane, so neither the copies nor the loads ever conflict.
  *             cp.async groups are per thread: no mbarrier, no cross-lane signalling, no uniform-datapath waterfall.
- *             Refill runs on a fixed schedule (every K records): a record consumes <= 77 bits, so a 64-word window
- *             refilled every 8 records always holds two service periods of look-ahead (see the proof at the loop).
+ *             Refill runs on a fixed schedule (every K records): a record consumes <= 77 bits, so a 32-word window
+ *             refilled every 4 records always holds two service periods of look-ahead (see the proof at the loop;
+ *             measured best of 32/4, 64/8, 64/4, 128/16 because it leaves the most warps resident).
  *   decode    stateless bit addressing: the 64 bits at bit position p are three LDS.32 at immediate row offsets + two
  *             funnel shifts (words are pre-swapped to native order by the repack); the '10' (window reuse) record —
  *             >95% of records on noisy-mantissa data — is then one shift + mask + xor and p += 2+m.
  *   reduce    window boundaries are row countdowns derived from the const-delta time page (no time decode and no
- *             division in the loop); partials stay in registers and are flushed to the same edge/cell arrays the
- *             general kernel uses, so k_fix_edges / k_merge_groups are shared and float sums keep the reference's
- *             left-to-right order.
+ *             division in the loop); when no lane reaches a boundary within the next K records — 14 rounds of 15 on
+ *             regular shards — the records run without the per-record boundary test.  Partials stay in registers and
+ *             are flushed to the same edge/cell arrays the general kernel uses, so k_fix_edges / k_merge_* are shared
+ *             and float sums keep the reference's left-to-right order.
+ * k_fused_raw takes the raw pages of the same columns (Gorilla output above 90 % of raw): warp per segment, lane per window.
  *
  * Earlier staging designs (per-lane TMA bulk copies, warp-cooperative cp.async + mbarriers) read the pages where they
  * lie; both spent more instructions on staging than on decoding — see profiles/r01_fast_kernel_history.md.
