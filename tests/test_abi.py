@@ -50,3 +50,30 @@ def test_product_never_references_the_oracle():
                    re.search(r"(#include|import|from)\s+[\"<\.\w/]*oracle", open(os.path.join(dirpath, f), errors="replace").read()):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, f"product files include/import the oracle: {bad}"
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every ABI struct as the C compiler sees include/ogpu.h == the ctypes mirror in _lib.py."""
+    import ctypes as C
+    import subprocess
+    pairs = {"og_filter_item": L.FilterItem, "og_call": L.Call, "og_query_desc": L.QueryDesc, "og_column_desc": L.ColumnDesc,
+             "og_shard_desc": L.ShardDesc, "og_colval_view": L.ColValView, "og_record_view": L.RecordView, "og_dense_col": L.DenseCol,
+             "og_dense_view": L.DenseView, "og_stats": L.Stats, "og_synth_column": L.SynthColumn, "og_synth_desc": L.SynthDesc,
+             "og_shard_layout": L.ShardLayout}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "ogpu.h")}"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _t in cls._fields_:
+            cfield = {"func": "func"}.get(fname, fname)
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {cfield}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = dict(line.split() for line in out.strip().splitlines())
+    for cname, cls in pairs.items():
+        assert int(seen[cname]) == C.sizeof(cls), cname
+        for fname, _t in cls._fields_:
+            assert int(seen[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
