@@ -272,7 +272,10 @@ OG_API int og_query_create(og_shard *s, const og_query_desc *d_in, og_query **ou
     d_clamped.tmin = std::max(d_in->tmin, MIN_TIME); d_clamped.tmax = std::min(d_in->tmax, MAX_TIME);
     const og_query_desc *d = &d_clamped;
     CU(cudaSetDevice(s->device));
-    if (!d->ascending) { set_error("descending scans are not supported on the GPU path"); return OG_E_UNSUPPORTED; }
+    /* ascending == 0 (ORDER BY time DESC): the windows and their aggregates are computed exactly as for an ascending scan and
+     * og_query_next emits the rows of every group from the latest window to the earliest.  Where the reference's reversed-record
+     * reduction could differ — which of two equal extremes inside one window lends its time to a single-call min/max, the
+     * association of float sums — the ascending rules apply (float sums stay within the 1e-9 bound). */
     if (d->n_calls == 0 || d->n_calls > OG_MAX_CALLS) { set_error("n_calls must be 1..%d", OG_MAX_CALLS); return OG_E_INVAL; }
     if (d->n_filter > OG_MAX_FILTER) { set_error("filter too long (max %d items)", OG_MAX_FILTER); return OG_E_INVAL; }
     if (d->interval < 0 || d->tmin > d->tmax) { set_error("bad interval or time range"); return OG_E_INVAL; }
@@ -797,11 +800,12 @@ OG_API int og_query_next(og_query *q, og_record_view *out) {
         /* a slice covers `chunk` interval rows; empty rows inside it are dropped */
         uint32_t b_end = (uint32_t)std::min<uint64_t>(p.n_buckets, (uint64_t)b + (uint64_t)chunk);
         for (; b < b_end; b++) {
-            size_t i = (size_t)g * p.n_buckets + b;
+            const uint32_t bb = q->desc.ascending ? b : p.n_buckets - 1 - b; /* descending: latest window first */
+            size_t i = (size_t)g * p.n_buckets + bb;
             bool any = false;
             for (uint32_t c = 0; c < nc; c++) any |= q->h_ok[c][i] != 0;
             if (!any) continue;
-            int64_t row_time = p.start + (int64_t)b * p.interval;
+            int64_t row_time = p.start + (int64_t)bb * p.interval;
             if (q->desc.interval == 0) row_time = 0;
             for (uint32_t c = 0; c < nc; c++) {
                 bool ok = q->h_ok[c][i] != 0;

@@ -162,7 +162,7 @@ class AggQuery:
     """calls: list of (func_name, column); filter: RPN list of ("term", column, op, const) | "and" | "or"."""
 
     def __init__(self, shard, calls, interval, tmin, tmax, offset=0, filter=None, group="all", series_group=None,
-                 n_groups=0, chunk_size=1024, flags=0):
+                 n_groups=0, chunk_size=1024, flags=0, ascending=True):
         self.shard = shard
         self._calls = (L.Call * len(calls))()
         for i, (f, c) in enumerate(calls):
@@ -183,7 +183,7 @@ class AggQuery:
                 else:
                     self._filter[i].const_is_float, self._filter[i].ival = 0, int(const)
         d = L.QueryDesc()
-        d.interval, d.offset, d.tmin, d.tmax, d.ascending = int(interval), int(offset), int(tmin), int(tmax), 1
+        d.interval, d.offset, d.tmin, d.tmax, d.ascending = int(interval), int(offset), int(tmin), int(tmax), 1 if ascending else 0
         d.n_calls, d.calls = len(calls), self._calls
         d.n_filter, d.filter = len(flt), self._filter
         d.group_mode = {"all": L.GROUP_ALL, "series": L.GROUP_PER_SERIES, "map": L.GROUP_MAP}[group]

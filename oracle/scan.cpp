@@ -183,7 +183,8 @@ int scan_aggregate(const og_shard_desc &sh, const og_query_desc &q_in, int threa
                    uint32_t series_end, ScanResult &out) {
     og_query_desc q = q_in; /* influxql.MinTime/MaxTime (ast.go:92,102) bound the range */
     q.tmin = std::max(q_in.tmin, (int64_t)(INT64_MIN + 2)); q.tmax = std::min(q_in.tmax, (int64_t)(INT64_MAX - 1));
-    if (!q.ascending) return E_UNSUPPORTED;
+    /* descending scans: the dense interval record holds the same aggregates; only the emission order of rows differs (it is not
+     * part of ScanResult).  The reference's reversed-record tie-breaks are NOT restated — parity unpinned for them. */
     if (series_end > sh.n_series) series_end = sh.n_series;
     /* schemas: the input record holds every column a call or the filter touches (+ time) */
     std::vector<int> cols;

@@ -223,12 +223,12 @@ def test_unsupported_and_corrupt_pages_fail_cleanly():
     with pytest.raises(L.OgpuError) as ei:
         _one_segment_shard(L.TYPE_INT, fpage, tp, t)
     assert ei.value.status == L.OG_E_TYPE
-    # descending scans are rejected, not mis-executed
+    # a call on a column that does not exist is rejected, not mis-executed
     sh = _one_segment_shard(L.TYPE_FLOAT, good, tp, t)
-    d = L.QueryDesc(); calls = (L.Call * 1)(); calls[0].func, calls[0].column = L.AGG_SUM, 0
-    d.interval, d.tmin, d.tmax, d.ascending, d.n_calls, d.calls = SEC, int(t[0]), int(t[-1]), 0, 1, calls
+    d = L.QueryDesc(); calls = (L.Call * 1)(); calls[0].func, calls[0].column = L.AGG_SUM, 7
+    d.interval, d.tmin, d.tmax, d.ascending, d.n_calls, d.calls = SEC, int(t[0]), int(t[-1]), 1, 1, calls
     h = C.c_void_p()
-    assert L.lib().og_query_create(sh.h, C.byref(d), C.byref(h)) == L.OG_E_UNSUPPORTED
+    assert L.lib().og_query_create(sh.h, C.byref(d), C.byref(h)) == L.OG_E_INVAL
     sh.close()
 
 

@@ -104,3 +104,34 @@ def test_gpu_returns_the_references_published_answers(case):
             assert g["cols"][0]["values"][0] == v and g["cols"][0]["times"][0] == t
             q.close()
     sh.close()
+
+
+def test_oracle_descending_scan_keeps_the_aggregates():
+    """ORDER BY time DESC changes the order rows are emitted in, not the windows' aggregates (server_test.go:2585-2590)."""
+    d = oracle.shard_desc_from_export(_export())
+    ca = (L.Call * 1)((L.AGG_MAX, 0))
+    res = []
+    for asc in (1, 0):
+        qd = L.QueryDesc(10 * SEC, 0, T2000, T2000 + 60 * SEC, asc, 1, ca, 0, None, L.GROUP_ALL, 1, None, 0, 0)
+        res.append(oracle.scan(d, qd, threads=1))
+    assert np.array_equal(res[0]["cols"][0]["values"], res[1]["cols"][0]["values"])
+    assert list(res[1]["cols"][0]["values"].view(np.float64)) == [2, 4, 4, 4, 5, 5, 7]
+
+
+@pytest.mark.gpu
+def test_gpu_order_by_time_desc():
+    """`SELECT max(value) ... group by time(10s) order by time desc` -> 7,5,5,4,4,4,2 from 00:01:00 down to 00:00:00 (server_test.go:2585-2590)."""
+    from opengemini_b200 import AggQuery, Shard
+    ex = _export()
+    sh = Shard.open(ex["data"], ex["sids"], ex["series_seg_begin"], ex["seg_tmin"], ex["seg_tmax"],
+                    [("value", L.TYPE_FLOAT, ex["page_off"][0], ex["page_len"][0])], ex["page_off"][1], ex["page_len"][1])
+    for chunk in (1024, 3):
+        q = AggQuery(sh, [("max", 0), ("count", 0)], 10 * SEC, T2000, T2000 + 60 * SEC, ascending=False, chunk_size=chunk).run()
+        vals, times = [], []
+        for rec in q.records():
+            assert rec["rows"] <= chunk
+            vals += list(rec["cols"][0]["values"]); times += list(rec["times"])
+        assert vals == [7, 5, 5, 4, 4, 4, 2]
+        assert times == [T2000 + k * 10 * SEC for k in range(6, -1, -1)]
+        q.close()
+    sh.close()
