@@ -25,7 +25,7 @@
  *   og_encode_pages          engine/immutable/column_builder.go:151-349 enc*Column + EncodeColumnHeader :428,
  *                            chunkdata_builder.go:65 EncodeTime (downsample / compaction re-encode).
  *   og_shard_synth           test/bench tooling: builds a synthetic shard directly in HBM with the encode kernels
- *                            (same bytes the oracle's restated encoders produce; see tests/test_synth_parity.py).
+ *                            (same bytes the oracle's restated encoders produce; see tests/test_gpu_parity.py::test_synth_pages_byte_exact).
  *
  * Conventions (modelled on the in-tree cgo precedents engine/index/textindex/textbuilder_c.h:20-28 and
  * lib/util/lifted/encoding/lz4/lz4_linux_amd64.go:18-30): opaque handles, caller-owned inputs, library-owned
@@ -52,7 +52,7 @@ enum {
     OG_E_INVAL = -1,       /* bad argument / descriptor */
     OG_E_CUDA = -2,        /* CUDA runtime failure or no device bound */
     OG_E_NOMEM = -3,
-    OG_E_UNSUPPORTED = -4, /* codec tag / option recognised but not implemented on the GPU path (zstd, mlf, lz4, descending, DST location) */
+    OG_E_UNSUPPORTED = -4, /* codec tag / option recognised but not implemented on the GPU path (zstd, mlf, lz4, DST location) */
     OG_E_CORRUPT = -5,     /* page failed validation (lib/errno InvalidFloatBuffer etc.) */
     OG_E_ABORTED = -6,     /* og_query_abort was called (closedSignal, engine/immutable/read_context.go:68-70) */
     OG_E_TYPE = -7,        /* "type(%v) in table not eq select type(%v)" column_builder.go:466 */
@@ -86,9 +86,12 @@ typedef struct og_call {
 
 enum { OG_GROUP_ALL = 0, OG_GROUP_PER_SERIES = 1, OG_GROUP_MAP = 2 };
 enum {
-    OG_Q_STRICT_ORDER = 1u << 0 /* cross-series float sums in strict series order (bit-exact with the reference's sequential
-                                   merge, lib/record/reccord_functions.go:730-733).  Every path of this version already folds
-                                   in that order, so the flag changes nothing today; it pins the behaviour for callers. */
+    OG_Q_STRICT_ORDER = 1u << 0 /* cross-series float sums in strict series order: bit-exact with the reference's sequential
+                                   merge (lib/record/reccord_functions.go:730-733).  Without it a one-tagset query on a regular
+                                   shard folds the series of a lane group with warp shuffles first (a fixed, reproducible
+                                   association; float sums then agree with the reference to ~1e-15 relative, inside the 1e-9
+                                   bound; counts, min/max/first/last and their times stay bit-exact).  Tag groups and
+                                   per-series output always use the strict order. */
     ,
     OG_Q_NO_FUSED = 1u << 1 /* force the generic materialise-tile path even when the fused kernel is eligible (testing / A-B) */
     ,
@@ -101,7 +104,8 @@ typedef struct og_query_desc {
     int64_t interval;  /* GROUP BY time() duration in ns; 0 = no interval (one window = [tmin, tmax]) */
     int64_t offset;    /* hybridqp.Interval.Offset */
     int64_t tmin, tmax;/* inclusive query time range (util.TimeRange) */
-    int32_t ascending; /* must be 1; descending scans return OG_E_UNSUPPORTED (SURVEY App.B.14) */
+    int32_t ascending; /* 1: ORDER BY time ASC; 0: ORDER BY time DESC (same windows and aggregates, og_query_next emits the latest
+                          window first).  NOTE: a zero-initialised descriptor therefore asks for descending output. */
     uint32_t n_calls;
     const og_call *calls;
     uint32_t n_filter; /* 0 = no WHERE on fields */
@@ -145,8 +149,8 @@ typedef struct og_shard_desc {
 
 /* ---- ColVal / Record views (lib/record/column.go:30-37, record.go:57-61) ---- */
 typedef struct og_colval_view {
-    const uint8_t *val;     /* dense interval records: one slot per row (AppendXxxNullReserve layout, record.go:1298-1338);
-                               decoded segments: non-null values only, densely packed LE (reader.go:504-579) */
+    const uint8_t *val;     /* non-null values only, densely packed LE — both for decoded segments (reader.go:504-579) and for the
+                               records og_query_next slices out of the interval record (TransIntervalRec2Rec, record.go:1340-1358) */
     uint64_t val_bytes;
     const uint8_t *bitmap;  /* LSB-first, 1 = present, bit index = bitmap_offset + row (column.go:26-28,489-498) */
     const int64_t *times;   /* RecMeta.Times[col] for first/last in multi-call queries, else NULL */
@@ -194,7 +198,15 @@ typedef struct og_stats {
     double h2d_ms;
     double main_kernel_ms;     /* of which: the dominant decode+reduce kernel(s) (k_fused_segment, or decode/filter/reduce tiles) */
     uint32_t kernel_launches;  /* kernels launched by the last og_query_run */
-    int32_t path;              /* 1 = fused kernel, 0 = generic materialise-tile path */
+    int32_t path;              /* 0 generic materialise-tile path; 1 fused, general per-segment kernel only; 2 fused Gorilla kernel over the
+                                  lane-interleaved copy with per-series cells (strict order / tag groups / per-series output);
+                                  3 the same with interior windows folded in-warp (one tagset, regular shard) */
+    int32_t il_state;          /* lane-interleaved copy of the queried float column: 1 ready, 0 not applicable, -1 no eligible page,
+                                  -2 NOT BUILT for lack of device memory (the query ran on the slower general kernel) */
+    int32_t per_series_cells_used; /* path 3 only: some lane group left the folded path (lanes out of step or irregular time grid) */
+    double il_build_ms;        /* one-off cost of building that copy (first query on the column) */
+    uint64_t il_bytes;         /* its size in HBM */
+    uint64_t general_segments; /* segments of the column that the Gorilla kernel does not take (other codecs, nulls, irregular time pages) */
 } og_stats;
 
 typedef struct og_shard og_shard;

@@ -34,15 +34,22 @@ struct DirP { /* device directory */
 struct ChunkP { /* one chunk of whole series */
     uint32_t series_begin, series_end; /* global series range */
     uint32_t seg_begin, seg_end;       /* global segment range (contiguous) */
-    Tri cells[OG_MAX_CALLS];           /* [ cell_idx(ch, series, b) ]: bucket-major, series contiguous — a warp whose lanes are
-                                          32 consecutive series writes one bucket as one 256-byte run */
-    uint32_t cell_sb;                  /* cells per bucket row = series of the chunk rounded up to 32 */
+    Tri cells[OG_MAX_CALLS];           /* per-series window partials [ cell_idx(ch, series, b) ]: series-major (the layout of the
+                                          per-series dense record), so a lane that walks its segment appends to one row whatever
+                                          series its neighbours hold, and a thread-per-bucket merge reads consecutive addresses */
+    uint32_t nb;                       /* buckets per series row (= QueryP.n_buckets) */
     Tri edges[OG_MAX_CALLS];           /* [ 2 * (seg - seg_begin) + {0 head, 1 tail} ] */
     uint32_t *edge_bucket;             /* [ 2 * (seg - seg_begin) ] OG_NO_BUCKET = absent */
+    Tri gcells[OG_MAX_CALLS];          /* folded window partials [ b * gc_cols + col ] (one tagset, regular shard): col < gc_edge0 is a
+                                          lane group of the fused kernel (32 series folded in-warp), col >= gc_edge0 a block of 32
+                                          consecutive series whose stitched edge windows k_fix_edges_fold folded.  nullptr when unused */
+    uint32_t gc_cols, gc_edge0, gc_col0;
+    uint32_t J;                        /* segments per series on a regular shard, else 0 */
     int *err;                          /* [0] first error code, [1] segment */
+    int *flags;                        /* [0] != 0: some kernel wrote per-series cells in this run (the cell merges have work) */
 };
 
-__device__ __forceinline__ size_t cell_idx(const ChunkP &ch, uint32_t series, uint32_t b) { return (size_t)b * ch.cell_sb + (series - ch.series_begin); }
+__device__ __forceinline__ size_t cell_idx(const ChunkP &ch, uint32_t series, uint32_t b) { return (size_t)(series - ch.series_begin) * ch.nb + b; }
 
 __device__ __forceinline__ void report_err(int *err, int code, uint32_t seg) {
     if (atomicCAS(&err[0], 0, code) == 0) err[1] = (int)seg;
@@ -54,6 +61,11 @@ __device__ __forceinline__ void store_part(const Tri &a, size_t i, const Part &p
 }
 __device__ __forceinline__ Part load_part(const Tri &a, size_t i) {
     Part p; p.ok = a.ok[i]; p.v = a.val[i]; p.t = a.tim ? a.tim[i] : 0; return p;
+}
+/* a per-series window partial; marks the cell matrix as in use */
+__device__ __forceinline__ void store_cell(const ChunkP &ch, int call, uint32_t series, uint32_t b, const Part &p) {
+    store_part(ch.cells[call], cell_idx(ch, series, b), p);
+    ch.flags[0] = 1;
 }
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -210,7 +222,7 @@ __device__ __forceinline__ void emit_window(const QueryP &q, const ChunkP &ch, u
                                             bool is_head, bool is_tail, int call, const Part &p) {
     if (is_head) store_part(ch.edges[call], 2 * (size_t)(seg - ch.seg_begin), p);
     else if (is_tail) store_part(ch.edges[call], 2 * (size_t)(seg - ch.seg_begin) + 1, p);
-    else if (p.ok) store_part(ch.cells[call], cell_idx(ch, series, b), p);
+    else if (p.ok) store_cell(ch, call, series, b, p);
 }
 
 /* step 3: one thread per segment walks its rows in time order (threads of a warp own consecutive segments and move row by row
@@ -231,7 +243,7 @@ __global__ void k_window_reduce(DirP d, QueryP q, TileP tp, ChunkP ch) {
         for (uint32_t c = 0; c < q.n_calls; c++) {
             if (!head_done) store_part(ch.edges[c], e, parts[c]);
             else if (final) store_part(ch.edges[c], e + 1, parts[c]);
-            else if (parts[c].ok) store_part(ch.cells[c], cell_idx(ch, series, cur_b), parts[c]);
+            else if (parts[c].ok) store_cell(ch, (int)c, series, cur_b, parts[c]);
         }
         if (!head_done) { head_done = true; head_b = cur_b; }
     };
@@ -261,42 +273,108 @@ __global__ void k_window_reduce(DirP d, QueryP q, TileP tp, ChunkP ch) {
 }
 
 /* ------------------------------------------------------------------------------------------------------------
- * ordered stitch of windows that span segment boundaries (thread per segment)
+ * ordered stitch of windows that span segment boundaries (prevBuf/currBuf, series_agg_reducer.gen.go:228-266)
  * ------------------------------------------------------------------------------------------------------------ */
+struct EdgeRuns { uint32_t hb, tb, s_end; bool head_leader; };
+/* the (up to two) windows of `seg` that may continue in neighbouring segments: its head window leads a run unless the previous
+ * segment's last window is the same bucket; its tail window always leads */
+__device__ __forceinline__ EdgeRuns edge_runs(const DirP &d, const ChunkP &ch, uint32_t seg, uint32_t series) {
+    EdgeRuns r;
+    const uint32_t s_first = d.series_seg_begin[series];
+    r.s_end = d.series_seg_begin[series + 1];
+    const uint32_t *eb = ch.edge_bucket;
+    const size_t e = 2 * (size_t)(seg - ch.seg_begin);
+    r.hb = eb[e]; r.tb = eb[e + 1];
+    r.head_leader = true;
+    if (r.hb != OG_NO_BUCKET && seg > s_first) { /* previous edge = tail(seg-1) if present else head(seg-1) */
+        const size_t pe = e - 2;
+        const uint32_t pb = eb[pe + 1] != OG_NO_BUCKET ? eb[pe + 1] : eb[pe];
+        if (pb != OG_NO_BUCKET && pb == r.hb) r.head_leader = false;
+    }
+    return r;
+}
+/* partial of the run led by edge `which` of `seg` for one call: ordered left-to-right merge of the edges of that bucket */
+__device__ __forceinline__ Part edge_stitch(const QueryP &q, const ChunkP &ch, const EdgeRuns &r, uint32_t seg, int which, uint32_t c) {
+    const CallP &cp = q.calls[c];
+    const uint32_t *eb = ch.edge_bucket;
+    const size_t e = 2 * (size_t)(seg - ch.seg_begin);
+    const uint32_t b = which == 0 ? r.hb : r.tb;
+    Part acc = load_part(ch.edges[c], e + which);
+    if (which == 1 || r.tb == OG_NO_BUCKET) { /* the run continues into later segments only from the last edge of this segment */
+        for (uint32_t nx = seg + 1; nx < r.s_end; nx++) {
+            const size_t ne = 2 * (size_t)(nx - ch.seg_begin);
+            if (eb[ne] != b) break; /* includes OG_NO_BUCKET */
+            acc = series_merge(cp.func, cp.type, acc, load_part(ch.edges[c], ne));
+            if (eb[ne + 1] != OG_NO_BUCKET) break; /* that segment has a distinct tail window: run ends at its head */
+        }
+    }
+    return acc;
+}
+
+/* thread per segment: stitched windows go to the per-series cells */
 __global__ void k_fix_edges(DirP d, QueryP q, ChunkP ch) {
     uint32_t seg = ch.seg_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= ch.seg_end) return;
-    uint32_t series = d.seg_series[seg];
-    uint32_t s_first = d.series_seg_begin[series], s_end = d.series_seg_begin[series + 1];
-    const uint32_t *eb = ch.edge_bucket;
-    size_t e = 2 * (size_t)(seg - ch.seg_begin);
-    uint32_t hb = eb[e], tb = eb[e + 1];
-    if (hb == OG_NO_BUCKET) return; /* no in-range rows */
-    /* is head(seg) the leader of its run?  previous edge = tail(seg-1) if present else head(seg-1) */
-    bool head_leader = true;
-    if (seg > s_first) {
-        size_t pe = e - 2;
-        uint32_t pb = eb[pe + 1] != OG_NO_BUCKET ? eb[pe + 1] : eb[pe];
-        if (pb != OG_NO_BUCKET && pb == hb) head_leader = false;
-    }
+    const uint32_t series = d.seg_series[seg];
+    const EdgeRuns r = edge_runs(d, ch, seg, series);
+    if (r.hb == OG_NO_BUCKET) return; /* no in-range rows */
     for (int which = 0; which < 2; which++) {
-        uint32_t b = which == 0 ? hb : tb;
-        if (which == 0 && !head_leader) continue;
-        if (which == 1 && tb == OG_NO_BUCKET) continue;
-        /* the run continues into later segments only from the last edge of this segment */
-        bool can_extend = which == 1 || tb == OG_NO_BUCKET;
+        if (which == 0 && !r.head_leader) continue;
+        if (which == 1 && r.tb == OG_NO_BUCKET) continue;
+        const uint32_t b = which == 0 ? r.hb : r.tb;
+        if (b >= q.n_buckets) { report_err(ch.err, D_CORRUPT, seg); continue; } /* a directory time range that lies about its page */
         for (uint32_t c = 0; c < q.n_calls; c++) {
-            const CallP &cp = q.calls[c];
-            Part acc = load_part(ch.edges[c], e + which);
-            if (can_extend) {
-                for (uint32_t nx = seg + 1; nx < s_end; nx++) {
-                    size_t ne = 2 * (size_t)(nx - ch.seg_begin);
-                    if (eb[ne] != b) break; /* includes OG_NO_BUCKET */
-                    acc = series_merge(cp.func, cp.type, acc, load_part(ch.edges[c], ne));
-                    if (eb[ne + 1] != OG_NO_BUCKET) break; /* that segment has a distinct tail window: run ends at its head */
-                }
-            }
-            if (acc.ok) store_part(ch.cells[c], cell_idx(ch, series, b), acc);
+            const Part acc = edge_stitch(q, ch, r, seg, which, c);
+            if (acc.ok) store_cell(ch, (int)c, series, b, acc);
+        }
+    }
+}
+
+__device__ __forceinline__ Part shfl_xor_part(const Part &p, int o, bool with_time) {
+    Part r; r.v = __shfl_xor_sync(0xffffffffu, p.v, o); r.ok = __shfl_xor_sync(0xffffffffu, p.ok, o);
+    r.t = with_time ? __shfl_xor_sync(0xffffffffu, p.t, o) : 0;
+    return r;
+}
+/* butterfly fold of 32 partials with the tagset update rules: group_update is commutative for count/sum and symmetric in its
+ * selector tie-breaks (equal value -> earlier time; equal time -> larger value), so every lane ends with the same cell */
+__device__ __forceinline__ Part warp_fold(int func, int type, bool multi, Part p, bool with_time) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const Part other = shfl_xor_part(p, o, with_time); group_update(func, type, multi, p, other); }
+    return p;
+}
+__device__ __forceinline__ bool call_has_time(const QueryP &q, uint32_t c) { return q.calls[c].func >= OG_AGG_MIN && !(q.multi && q.calls[c].func <= OG_AGG_MAX); }
+__device__ __forceinline__ int call_ftype(const QueryP &q, uint32_t c) { return q.calls[c].func == OG_AGG_COUNT ? OG_TYPE_INT : q.calls[c].type; }
+
+/* regular shards, one tagset: warp per (block of 32 consecutive series, segment index); the lanes' stitched windows of one
+ * bucket are folded in-warp into ONE cell of the folded matrix (column gc_edge0 + block).  Blocks whose series do not agree
+ * on the bucket (irregular time grids) fall back to per-series cells. */
+__global__ void k_fix_edges_fold(DirP d, QueryP q, ChunkP ch) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_blk = (ch.series_end - ch.series_begin + 31) / 32;
+    if (w >= n_blk * ch.J) return;
+    const uint32_t blk = w / ch.J, j = w % ch.J;
+    const uint32_t series = ch.series_begin + blk * 32 + lane;
+    const bool in = series < ch.series_end;
+    const uint32_t seg = in ? d.series_seg_begin[series] + j : 0;
+    EdgeRuns r; r.hb = r.tb = OG_NO_BUCKET; r.head_leader = false; r.s_end = 0;
+    if (in) r = edge_runs(d, ch, seg, series);
+    const uint32_t gcol = ch.gc_edge0 + ch.series_begin / 32 + blk - ch.gc_col0;
+    for (int which = 0; which < 2; which++) {
+        const bool has = r.hb != OG_NO_BUCKET && (which == 0 ? r.head_leader : r.tb != OG_NO_BUCKET);
+        const uint32_t b = which == 0 ? r.hb : r.tb;
+        const uint32_t hm = __ballot_sync(0xffffffffu, has);
+        if (hm == 0) continue;
+        const int leader = __ffs(hm) - 1;
+        const uint32_t bL = __shfl_sync(0xffffffffu, b, leader);
+        const bool unif = __all_sync(0xffffffffu, !has || b == bL) && bL < q.n_buckets;
+        if (!unif && has && b >= q.n_buckets) { report_err(ch.err, D_CORRUPT, seg); continue; }
+        for (uint32_t c = 0; c < q.n_calls; c++) {
+            Part acc = part_empty();
+            if (has) acc = edge_stitch(q, ch, r, seg, which, c);
+            if (unif) {
+                acc = warp_fold(q.calls[c].func, call_ftype(q, c), q.multi != 0, acc, call_has_time(q, c));
+                if ((int)lane == leader && acc.ok) store_part(ch.gcells[c], (size_t)bL * ch.gc_cols + gcol, acc);
+            } else if (has && acc.ok) store_cell(ch, (int)c, series, b, acc);
         }
     }
 }
@@ -312,6 +390,7 @@ struct GroupP {
 };
 
 __global__ void k_merge_groups(QueryP q, ChunkP ch, GroupP gp) {
+    if (ch.flags[0] == 0) return; /* no per-series cell was written */
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)gp.n_groups * q.n_buckets;
     if (idx >= total) return;
@@ -330,7 +409,7 @@ __global__ void k_merge_groups(QueryP q, ChunkP ch, GroupP gp) {
         const Tri cells = ch.cells[c];
         /* The fold is strictly sequential in series order (that is the reference's order, reccord_functions.go:730-733),
          * but the loads do not depend on it: fetch a batch of U partials first, so each thread keeps U independent
-         * loads in flight (16,667 bucket threads alone cannot hide DRAM latency). */
+         * loads in flight.  Threads of a warp own consecutive buckets: every load is a coalesced run of one series row. */
         constexpr int U = 16;
         for (uint32_t i = lo; i < hi; i += U) {
             uint32_t okv[U]; uint64_t vv[U]; int64_t tt[U];
@@ -341,8 +420,8 @@ __global__ void k_merge_groups(QueryP q, ChunkP ch, GroupP gp) {
                 bool in = s < ch.series_end;
                 size_t ci = in ? cell_idx(ch, s, b) : 0;
                 okv[u] = in ? cells.ok[ci] : 0;
-                vv[u] = in ? cells.val[ci] : 0;
-                tt[u] = (in && cells.tim) ? cells.tim[ci] : 0;
+                vv[u] = okv[u] ? cells.val[ci] : 0;
+                tt[u] = (okv[u] && cells.tim) ? cells.tim[ci] : 0;
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -355,72 +434,42 @@ __global__ void k_merge_groups(QueryP q, ChunkP ch, GroupP gp) {
     }
 }
 
-/* k_merge_groups for the one-tagset case (OG_GROUP_ALL) when no call carries a time: the cell matrix is bucket-major with
- * the series contiguous, so a block stages a [128 buckets][32 series] tile through shared memory with fully coalesced 256-byte
- * row loads, then thread t folds row t left to right — the same strictly sequential series order as k_merge_groups. */
-__global__ void __launch_bounds__(128) k_merge_all(QueryP q, ChunkP ch, GroupP gp) {
-    __shared__ uint64_t sv[128 * 33];
-    __shared__ uint8_t sk[128 * 36];
-    const uint32_t c = blockIdx.y, b0 = blockIdx.x * 128, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const uint32_t nS = ch.series_end - ch.series_begin, nb = q.n_buckets;
+/* OG_GROUP_PER_SERIES: every tagset is one series and the cell matrix already has the dense record's layout, so the merge
+ * is elementwise: each cell goes through group_update on an empty accumulator (same value/time rules as the general merge). */
+__global__ void k_merge_per_series(QueryP q, ChunkP ch, GroupP gp) {
+    const uint32_t c = blockIdx.y;
+    const size_t n = (size_t)(ch.series_end - ch.series_begin) * q.n_buckets;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
     const CallP &cp = q.calls[c];
     const int ftype = cp.out_type == OG_TYPE_INT && cp.func == OG_AGG_COUNT ? OG_TYPE_INT : cp.type;
-    const Tri cells = ch.cells[c];
-    Part acc = part_empty();
-    if (b0 + t < nb) acc = load_part(gp.dense[c], b0 + t);
-    for (uint32_t s0 = 0; s0 < nS; s0 += 32) {
-        const uint32_t sr = s0 + lane;
-#pragma unroll 16
-        for (uint32_t i = 0; i < 32; i++) {
-            const uint32_t r = w + 4 * i, b = b0 + r;
-            const bool in = b < nb && sr < nS;
-            const size_t ci = in ? (size_t)b * ch.cell_sb + sr : 0;
-            const uint8_t k = in ? cells.ok[ci] : (uint8_t)0;
-            sv[r * 33 + lane] = in ? cells.val[ci] : 0;
-            sk[r * 36 + lane] = k;
-        }
-        __syncthreads();
-        if (b0 + t < nb) {
-#pragma unroll 8
-            for (uint32_t k = 0; k < 32; k++) {
-                if (!sk[t * 36 + k]) continue;
-                Part p; p.ok = 1; p.v = sv[t * 33 + k]; p.t = 0;
-                group_update(cp.func, ftype, q.multi != 0, acc, p);
-            }
-        }
-        __syncthreads();
-    }
-    if (b0 + t < nb) store_part(gp.dense[c], b0 + t, acc);
+    const uint32_t b = (uint32_t)(i % q.n_buckets);
+    Part p; p.ok = ch.cells[c].ok[i]; p.v = p.ok ? ch.cells[c].val[i] : 0; p.t = (p.ok && ch.cells[c].tim) ? ch.cells[c].tim[i] : 0;
+    Part a; a.v = 0; a.ok = 0; a.t = q.multi ? 0 : q.start + (int64_t)b * q.interval;
+    group_update(cp.func, ftype, q.multi != 0, a, p);
+    store_part(gp.dense[c], (size_t)ch.series_begin * q.n_buckets + i, a);
 }
 
-/* OG_GROUP_PER_SERIES: every tagset is one series, so the merge is a transposition of the bucket-major cell matrix into the
- * series-major dense record — done through a 32x32 shared-memory tile so both sides are coalesced.  Each element still goes
- * through group_update on an empty accumulator (same value/time rules as the general merge); k_init_dense is not needed. */
-__global__ void __launch_bounds__(256) k_merge_per_series(QueryP q, ChunkP ch, GroupP gp) {
-    __shared__ uint64_t sv[32][33];
-    __shared__ int64_t st[32][33];
-    __shared__ uint8_t sk[32][36];
-    const uint32_t c = blockIdx.z, b0 = blockIdx.x * 32, s0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
-    const uint32_t nS = ch.series_end - ch.series_begin, nb = q.n_buckets;
-    const CallP &cp = q.calls[c];
-    const int ftype = cp.out_type == OG_TYPE_INT && cp.func == OG_AGG_COUNT ? OG_TYPE_INT : cp.type;
-    const Tri cells = ch.cells[c];
-    for (uint32_t j = ty; j < 32; j += 8) {
-        const uint32_t b = b0 + j, sr = s0 + tx;
-        const bool in = b < nb && sr < nS;
-        const size_t ci = in ? (size_t)b * ch.cell_sb + sr : 0;
-        sk[j][tx] = in ? cells.ok[ci] : (uint8_t)0;
-        sv[j][tx] = in ? cells.val[ci] : 0;
-        st[j][tx] = (in && cells.tim) ? cells.tim[ci] : 0;
+/* one tagset: dense[b] (+)= fold over the columns of the folded cell matrix (warp per bucket, grid.y = call; lanes take
+ * columns lane, lane+32, ... in order, then a butterfly: a fixed association, so results are reproducible run to run) */
+__global__ void k_merge_folded(QueryP q, ChunkP ch, GroupP gp) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, c = blockIdx.y;
+    if (b >= q.n_buckets) return;
+    const int func = q.calls[c].func, ftype = call_ftype(q, c);
+    const bool wt = call_has_time(q, c), multi = q.multi != 0;
+    const Tri g = ch.gcells[c];
+    Part acc = part_empty();
+    const size_t row = (size_t)b * ch.gc_cols;
+    for (uint32_t col = lane; col < ch.gc_cols; col += 32) {
+        if (!g.ok[row + col]) continue;
+        Part p; p.ok = 1; p.v = g.val[row + col]; p.t = wt ? g.tim[row + col] : 0;
+        group_update(func, ftype, multi, acc, p);
     }
-    __syncthreads();
-    for (uint32_t j = ty; j < 32; j += 8) {
-        const uint32_t sr = s0 + j, b = b0 + tx;
-        if (sr >= nS || b >= nb) continue;
-        Part p; p.ok = sk[tx][j]; p.v = sv[tx][j]; p.t = st[tx][j];
-        Part a; a.v = 0; a.ok = 0; a.t = q.multi ? 0 : q.start + (int64_t)b * q.interval;
-        group_update(cp.func, ftype, q.multi != 0, a, p);
-        store_part(gp.dense[c], (size_t)(ch.series_begin + sr) * nb + b, a);
+    acc = warp_fold(func, ftype, multi, acc, wt);
+    if (lane == 0 && acc.ok) {
+        Part a = load_part(gp.dense[c], b);
+        group_update(func, ftype, multi, a, acc);
+        store_part(gp.dense[c], b, a);
     }
 }
 

@@ -10,7 +10,8 @@
 
 #include "agg_kernels.cuh"
 #include "fused.cuh"
-#include "fused_fast.cuh"
+#include "il_build.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include "internal.h"
 
 namespace ogpu {
@@ -29,6 +30,7 @@ static int map_dev_err(int code) {
     switch (code) {
     case D_UNSUPPORTED: return OG_E_UNSUPPORTED;
     case D_TYPE: return OG_E_TYPE;
+    case D_WATCHDOG: return OG_E_CUDA;
     default: return OG_E_CORRUPT;
     }
 }
@@ -134,7 +136,10 @@ OG_API void og_shard_close(og_shard *s) {
     cudaFree(s->d_page_off); cudaFree(s->d_page_len); cudaFree(s->d_sids);
     if (s->h_seg_buf) cudaFreeHost(s->h_seg_buf);
     if (s->d_seg_buf) cudaFree(s->d_seg_buf);
-    for (auto &c : s->il) { cudaFree(c.words); cudaFree(c.grp_off); cudaFree(c.grp_words); cudaFree(c.ok); cudaFree(c.lane_seg); }
+    for (auto &c : s->il) {
+        cudaFree(c.words); cudaFree(c.grp_off); cudaFree(c.grp_rows); cudaFree(c.grp_col); cudaFree(c.ok); cudaFree(c.lane_seg); cudaFree(c.lane_rows);
+        cudaFree(c.lane_series); cudaFree(c.lane_t0); cudaFree(c.lane_dt); cudaFree(c.gen_list);
+    }
     delete s;
 }
 
@@ -360,52 +365,50 @@ namespace {
 struct Plan { /* built once per query, reused by every og_query_run */
     ChunkP ch; TileP tp; GroupP gp;
     bool fused;
-    uint8_t *cls;   /* per-segment class (SEG_FAST / SEG_GENERAL) when the fast Gorilla kernel applies, else nullptr */
+    bool fast;      /* the fused Gorilla kernel serves the eligible segments, k_fused_segment the rest */
+    bool fold;      /* interior windows are folded in-warp into gcells (one tagset, regular shard, no strict order) */
     int fm; bool times;
-    IlP il; uint32_t il_groups, il_J;
-    uint32_t *cls_list[2];              /* device: sorted ids of the SEG_GENERAL [0] / SEG_RAW [1] segments (k_fused_segment / k_fused_raw) */
-    std::vector<uint32_t> *cls_host[2]; /* same, on the host (per-chunk ranges are found by binary search) */
+    IlP il;
+    const og_shard::IlCol *ic;
 };
-void free_plan(void *plan) { Plan *pl = (Plan *)plan; if (pl) { delete pl->cls_host[0]; delete pl->cls_host[1]; delete pl; } }
+void free_plan(void *plan) { delete (Plan *)plan; }
 template <class T> int salloc(og_query *q, T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) q->scratch.push_back(*p); return rc; }
 
 template <int NC> void launch_fused(const DirP &d, const QueryP &p, const ChunkP &ch, const uint32_t *list, uint32_t n, cudaStream_t st) {
     if (n) k_fused_segment<NC><<<(n + 127) / 128, 128, 0, st>>>(d, p, ch, list, n);
 }
-struct FastArgs { IlP il; uint32_t n_groups, segs_per_series; };
-template <int FM, bool TIMES> void launch_fast_t(const FastArgs &fa, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
-    /* lane groups of this chunk: 32-series blocks x segment index on regular shards (chunks are multiples of 32 series),
-     * else 32 consecutive segments (a group that straddles the chunk boundary runs with the lanes of this chunk) */
-    uint32_t g0, g1;
-    if (fa.segs_per_series) { g0 = (ch.series_begin / 32) * fa.segs_per_series; g1 = ((ch.series_end + 31) / 32) * fa.segs_per_series; }
-    else { g0 = ch.seg_begin / 32; g1 = (ch.seg_end + 31) / 32; }
-    g1 = std::min(g1, fa.n_groups);
+template <int FM, bool TIMES> void launch_fast_t(bool fold, const IlP &il, uint32_t g0, uint32_t g1, const QueryP &p, const ChunkP &ch, cudaStream_t st) {
     constexpr uint32_t WPB = OG_FAST_THREADS / 32;
     dim3 grid((g1 - g0 + WPB - 1) / WPB), block(OG_FAST_THREADS);
-    k_fused_fast<FM, TIMES><<<grid, block, 0, st>>>(d, p, ch, cls, fa.il, g0, g1);
+    if (fold) k_fused_il<FM, TIMES, true><<<grid, block, WPB * il_acc_bytes(p.n_calls, TIMES), st>>>(p, ch, il, g0, g1);
+    else k_fused_il<FM, TIMES, false><<<grid, block, 0, st>>>(p, ch, il, g0, g1);
 }
 /* a handful of aggregate-set specialisations; anything else runs the all-aggregates instance */
-void launch_fast(int fm, bool times, const FastArgs &stage, const DirP &d, const QueryP &p, const ChunkP &ch, const uint8_t *cls, cudaStream_t st) {
+void launch_fast(int fm, bool times, bool fold, const IlP &il, uint32_t g0, uint32_t g1, const QueryP &p, const ChunkP &ch, cudaStream_t st) {
+    if (g1 <= g0) return;
     if (!times) {
         switch (fm) {
-        case FM_SUM | FM_COUNT: return launch_fast_t<FM_SUM | FM_COUNT, false>(stage, d, p, ch, cls, st);
-        case FM_SUM | FM_COUNT | FM_MAX: return launch_fast_t<FM_SUM | FM_COUNT | FM_MAX, false>(stage, d, p, ch, cls, st);
-        case FM_SUM | FM_COUNT | FM_MIN | FM_MAX: return launch_fast_t<FM_SUM | FM_COUNT | FM_MIN | FM_MAX, false>(stage, d, p, ch, cls, st);
-        case FM_COUNT: return launch_fast_t<FM_COUNT, false>(stage, d, p, ch, cls, st);
+        case FM_SUM | FM_COUNT: return launch_fast_t<FM_SUM | FM_COUNT, false>(fold, il, g0, g1, p, ch, st);
+        case FM_SUM | FM_COUNT | FM_MAX: return launch_fast_t<FM_SUM | FM_COUNT | FM_MAX, false>(fold, il, g0, g1, p, ch, st);
+        case FM_SUM | FM_COUNT | FM_MIN | FM_MAX: return launch_fast_t<FM_SUM | FM_COUNT | FM_MIN | FM_MAX, false>(fold, il, g0, g1, p, ch, st);
+        case FM_COUNT: return launch_fast_t<FM_COUNT, false>(fold, il, g0, g1, p, ch, st);
         default: break;
         }
     } else {
         switch (fm) {
-        case FM_MAX | FM_COUNT: return launch_fast_t<FM_MAX | FM_COUNT, true>(stage, d, p, ch, cls, st);
-        case FM_MIN | FM_COUNT: return launch_fast_t<FM_MIN | FM_COUNT, true>(stage, d, p, ch, cls, st);
+        case FM_MAX | FM_COUNT: return launch_fast_t<FM_MAX | FM_COUNT, true>(fold, il, g0, g1, p, ch, st);
+        case FM_MIN | FM_COUNT: return launch_fast_t<FM_MIN | FM_COUNT, true>(fold, il, g0, g1, p, ch, st);
         default: break;
         }
     }
-    return launch_fast_t<63, true>(stage, d, p, ch, cls, st);
+    return launch_fast_t<63, true>(fold, il, g0, g1, p, ch, st);
 }
 
-/* Build (once per shard and column) the lane-interleaved stream copy that k_fused_fast reads.  Returns OG_OK with
- * state 1 (ready) or -1 (nothing eligible / not enough memory: the general fused kernel serves the column instead). */
+struct TmpBufs { std::vector<void *> v; ~TmpBufs() { for (void *p : v) cudaFree(p); } template <class T> int get(T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) v.push_back(*p); return rc; } };
+
+/* Build (once per shard and column) the lane-interleaved, length-binned stream copy that k_fused_il reads (il_build.cuh).
+ * Returns OG_OK with state 1 (ready), -1 (nothing eligible) or -2 (not enough device memory: the general fused kernel
+ * serves the column instead; visible in og_stats.il_state). */
 int ensure_il(og_shard *s, int col, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(s->il_mu);
     if (s->il.size() != s->n_columns) s->il.resize(s->n_columns);
@@ -413,50 +416,94 @@ int ensure_il(og_shard *s, int col, cudaStream_t st) {
     if (ic.state != 0) return OG_OK;
     ic.state = -1;
     if (s->n_segments == 0 || s->col_types[col] != OG_TYPE_FLOAT) return OG_OK;
-    /* lane groups: segment j of 32 consecutive series when every series has the same number of segments, else 32 consecutive segments */
+    const uint32_t nseg = s->n_segments;
+    /* regular shard: every series has the same number of segments -> lane groups share a segment index */
     uint32_t J = s->n_series ? s->h_series_seg_begin[1] - s->h_series_seg_begin[0] : 0;
     for (uint32_t i = 0; i < s->n_series && J; i++) if (s->h_series_seg_begin[i + 1] - s->h_series_seg_begin[i] != J) J = 0;
-    const uint32_t ng = J ? ((s->n_series + 31) / 32) * J : (s->n_segments + 31) / 32;
-    {
-        std::vector<uint32_t> ls((size_t)ng * 32, OG_IL_NONE);
-        if (J) {
-            for (uint32_t sr = 0; sr < s->n_series; sr++)
-                for (uint32_t j = 0; j < J; j++) ls[((size_t)(sr / 32) * J + j) * 32 + (sr & 31)] = s->h_series_seg_begin[sr] + j;
-        } else for (uint32_t g = 0; g < s->n_segments; g++) ls[g] = g;
-        int rc0;
-        if ((rc0 = dalloc(&ic.lane_seg, ls.size()))) return rc0;
-        CU(cudaMemcpy(ic.lane_seg, ls.data(), ls.size() * 4, cudaMemcpyHostToDevice));
-    }
-    ic.n_groups = ng; ic.segs_per_series = J;
-    uint32_t *seg_words = nullptr;
+    const uint32_t n_super = J ? (s->n_series + OG_IL_SUPER - 1) / OG_IL_SUPER : 1;
+    const uint64_t n_dom64 = J ? (uint64_t)n_super * J : 1;
+    if (n_dom64 >= (1ull << 31)) return OG_OK;
+    const uint32_t n_dom = (uint32_t)n_dom64;
     int rc;
-    struct Ev { cudaEvent_t e = nullptr; Ev() { cudaEventCreate(&e); } ~Ev() { if (e) cudaEventDestroy(e); } } ev0, ev1; /* destroyed on every return path */
-    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
-    cudaEventRecord(e0, st);
-    if ((rc = dalloc(&ic.ok, (size_t)s->n_segments))) return rc;
-    if ((rc = dalloc(&seg_words, (size_t)s->n_segments))) return rc;
-    struct Free { void *p; ~Free() { cudaFree(p); } } free_seg_words{seg_words};
-    if ((rc = dalloc(&ic.grp_words, (size_t)ng))) return rc;
-    if ((rc = dalloc(&ic.grp_off, (size_t)ng))) return rc;
+    struct Ev { cudaEvent_t e = nullptr; Ev() { cudaEventCreate(&e); } ~Ev() { if (e) cudaEventDestroy(e); } } ev0, ev1;
+    cudaEventRecord(ev0.e, st);
+    TmpBufs tmp;
+    IlScanOut so{};
+    uint32_t *seg_words; uint64_t *keys2; uint32_t *vals2;
+    if ((rc = dalloc(&ic.ok, (size_t)nseg))) return rc;
+    so.ok = ic.ok;
+    if ((rc = tmp.get(&seg_words, nseg)) || (rc = tmp.get(&so.seg_t0, nseg)) || (rc = tmp.get(&so.seg_dt, nseg)) || (rc = tmp.get(&so.keys, nseg)) ||
+        (rc = tmp.get(&so.vals, nseg)) || (rc = tmp.get(&keys2, nseg)) || (rc = tmp.get(&vals2, nseg)) || (rc = tmp.get(&so.dom_cnt, n_dom))) return rc;
+    so.seg_words = seg_words;
+    CU(cudaMemsetAsync(so.dom_cnt, 0, (size_t)n_dom * 4, st));
     DirP d = make_dir(s);
-    k_il_scan<<<(s->n_segments + 255) / 256, 256, 0, st>>>(d, col, s->col_types[col], ic.ok, seg_words);
-    k_il_group_words<<<(unsigned)(((size_t)ng * 32 + 255) / 256), 256, 0, st>>>(ng, ic.lane_seg, seg_words, ic.grp_words);
+    k_il_scan<<<(nseg + 255) / 256, 256, 0, st>>>(d, col, s->col_types[col], J, so);
+    CU(cudaGetLastError());
+    /* stable sort by (domain, words): not-eligible segments (key ~0) end up last, in segment order */
+    int dbits = 1; while ((1ull << dbits) < n_dom64 + 1) dbits++;
+    {
+        size_t tb = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, so.keys, keys2, so.vals, vals2, (int)nseg, 0, (int)OG_IL_WORD_BITS + dbits, st));
+        void *dtmp; if ((rc = tmp.get((uint8_t **)&dtmp, tb))) return rc;
+        CU(cub::DeviceRadixSort::SortPairs(dtmp, tb, so.keys, keys2, so.vals, vals2, (int)nseg, 0, (int)OG_IL_WORD_BITS + dbits, st));
+    }
+    std::vector<uint32_t> dom_cnt(n_dom);
+    CU(cudaMemcpyAsync(dom_cnt.data(), so.dom_cnt, (size_t)n_dom * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<uint32_t> elem_first(n_dom), grp_first(n_dom);
+    uint64_t n_elig = 0, ng64 = 0;
+    for (uint32_t i = 0; i < n_dom; i++) { elem_first[i] = (uint32_t)n_elig; grp_first[i] = (uint32_t)ng64; n_elig += dom_cnt[i]; ng64 += (dom_cnt[i] + 31) / 32; }
+    /* the segments the fused kernel does not take: the tail of the sorted order */
+    const uint32_t n_gen = nseg - (uint32_t)n_elig;
+    if (n_gen) {
+        if ((rc = dalloc(&ic.gen_list, (size_t)n_gen))) return rc;
+        CU(cudaMemcpyAsync(ic.gen_list, vals2 + n_elig, (size_t)n_gen * 4, cudaMemcpyDeviceToDevice, st));
+        ic.gen_host.resize(n_gen);
+        CU(cudaMemcpyAsync(ic.gen_host.data(), vals2 + n_elig, (size_t)n_gen * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (n_elig == 0) return OG_OK;
+    const uint32_t ng = (uint32_t)ng64;
+    ic.n_groups = ng; ic.J = J; ic.n_super = n_super; ic.cols_per_super = OG_IL_SUPER / 32 + 1;
+    ic.super_grp_first.assign(n_super + 1, ng);
+    for (uint32_t sp = 0; sp < n_super; sp++) ic.super_grp_first[sp] = grp_first[J ? sp * J : 0];
+    uint32_t *d_elem_first, *d_grp_first;
+    if ((rc = tmp.get(&d_elem_first, n_dom)) || (rc = tmp.get(&d_grp_first, n_dom))) return rc;
+    CU(cudaMemcpyAsync(d_elem_first, elem_first.data(), (size_t)n_dom * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_grp_first, grp_first.data(), (size_t)n_dom * 4, cudaMemcpyHostToDevice, st));
+    const size_t n_slots = (size_t)ng * 32;
+    if ((rc = dalloc(&ic.lane_seg, n_slots)) || (rc = dalloc(&ic.lane_rows, n_slots)) || (rc = dalloc(&ic.lane_series, n_slots)) ||
+        (rc = dalloc(&ic.lane_t0, n_slots)) || (rc = dalloc(&ic.lane_dt, n_slots)) || (rc = dalloc(&ic.grp_col, (size_t)ng)) ||
+        (rc = dalloc(&ic.grp_rows, (size_t)ng)) || (rc = dalloc(&ic.grp_off, (size_t)ng))) return rc;
+    CU(cudaMemsetAsync(ic.lane_seg, 0xff, n_slots * 4, st));
+    CU(cudaMemsetAsync(ic.lane_rows, 0, n_slots * 4, st));
+    IlAssign as{};
+    as.keys = keys2; as.segs = vals2; as.elem_first = d_elem_first; as.grp_first = d_grp_first;
+    as.seg_words = seg_words; as.seg_t0 = so.seg_t0; as.seg_dt = so.seg_dt; as.ok = ic.ok;
+    as.lane_seg = ic.lane_seg; as.lane_rows = ic.lane_rows; as.lane_series = ic.lane_series; as.grp_col = ic.grp_col; as.lane_t0 = ic.lane_t0; as.lane_dt = ic.lane_dt;
+    as.n_elig = (uint32_t)n_elig; as.J = J; as.cols_per_super = ic.cols_per_super;
+    k_il_assign<<<(unsigned)((n_elig + 255) / 256), 256, 0, st>>>(d, as);
+    k_il_group_rows<<<(unsigned)((n_slots + 255) / 256), 256, 0, st>>>(ng, ic.lane_seg, seg_words, ic.grp_rows);
+    CU(cudaGetLastError());
     std::vector<uint32_t> gw(ng); std::vector<uint64_t> go(ng);
-    CU(cudaMemcpyAsync(gw.data(), ic.grp_words, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(gw.data(), ic.grp_rows, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     uint64_t total = 0;
     for (uint32_t g = 0; g < ng; g++) { go[g] = total; total += (uint64_t)gw[g] * 32; }
-    if (total == 0) return OG_OK;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    if (total * 4 + ((size_t)8 << 30) > free_b) return OG_OK; /* keep headroom for the query scratch: fall back to the general kernel */
-    if (cudaMalloc(&ic.words, total * 4) != cudaSuccess) { cudaGetLastError(); ic.words = nullptr; return OG_OK; }
+    size_t headroom = (size_t)8 << 30;
+    if (const char *ov = getenv("OGPU_IL_HEADROOM_MB")) headroom = (size_t)atoll(ov) << 20; /* test hook */
+    if (total * 4 + headroom > free_b || cudaMalloc(&ic.words, total * 4) != cudaSuccess) { /* keep room for the query scratch: the general kernel serves the column */
+        cudaGetLastError(); ic.words = nullptr; ic.state = -2;
+        return OG_OK;
+    }
     CU(cudaMemcpyAsync(ic.grp_off, go.data(), (size_t)ng * 8, cudaMemcpyHostToDevice, st));
-    k_il_repack<<<(unsigned)(((size_t)ng * 32 + 127) / 128), 128, 0, st>>>(d, col, ic.ok, ic.lane_seg, ic.grp_off, ic.grp_words, ng, ic.words);
+    k_il_repack<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(d, col, ic.ok, ic.lane_seg, ic.grp_off, ic.grp_rows, ng, ic.words);
     CU(cudaGetLastError());
-    cudaEventRecord(e1, st);
+    cudaEventRecord(ev1.e, st);
     CU(cudaStreamSynchronize(st));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    float ms = 0; cudaEventElapsedTime(&ms, ev0.e, ev1.e);
     ic.n_words = total; ic.build_ms = ms; ic.state = 1;
     return OG_OK;
 }
@@ -467,7 +514,7 @@ int build_plan(og_query *q) {
     cudaStream_t st = q->stream;
     int rc;
     Plan *pl = new Plan;
-    memset(pl, 0, sizeof *pl);
+    memset((void *)pl, 0, sizeof *pl);
     q->plan = pl;
     size_t cells_dense = (size_t)q->n_groups * p.n_buckets;
     for (uint32_t c = 0; c < p.n_calls; c++) { /* dense accumulators (the result) */
@@ -490,12 +537,21 @@ int build_plan(og_query *q) {
     uint32_t *d_grp_begin, *d_grp_series;
     if ((rc = salloc(q, &d_grp_begin, grp_begin.size()))) return rc;
     if ((rc = salloc(q, &d_grp_series, grp_series.size()))) return rc;
-    if ((rc = salloc(q, &q->d_err, 2))) return rc;
+    if ((rc = salloc(q, &q->d_err, 4))) return rc;
     CU(cudaMemcpyAsync(d_grp_begin, grp_begin.data(), grp_begin.size() * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_grp_series, grp_series.data(), grp_series.size() * 4, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st)); /* the host vectors die with this frame */
     pl->gp.grp_begin = d_grp_begin; pl->gp.grp_series = d_grp_series; pl->gp.n_groups = q->n_groups;
     for (uint32_t c = 0; c < p.n_calls; c++) pl->gp.dense[c] = q->dense[c];
+
+    pl->fused = p.n_cols == 1 && p.n_filter == 0 && !(q->desc.flags & OG_Q_NO_FUSED);
+    q->path_used = pl->fused ? 1 : 0;
+    const bool want_fast = pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments;
+    if (want_fast && (rc = ensure_il(s, p.col_index[0], st))) return rc;
+    pl->fast = want_fast && s->il[p.col_index[0]].state == 1;
+    const og_shard::IlCol *ic = pl->fast ? &s->il[p.col_index[0]] : nullptr;
+    pl->ic = ic;
+    pl->fold = pl->fast && ic->J != 0 && q->desc.group_mode == OG_GROUP_ALL && !(q->desc.flags & OG_Q_STRICT_ORDER);
 
     /* chunk plan: whole series per chunk, per-series cells bounded by a memory budget */
     size_t cell_bytes_per_series = 0;
@@ -508,16 +564,21 @@ int build_plan(og_query *q) {
         long v = atol(ov);
         if (v > 0) q->chunk_series = (uint32_t)std::min<long>(v, (long)std::max<uint32_t>(1, s->n_series));
     }
-    if (q->chunk_series < s->n_series) q->chunk_series = std::max<uint32_t>(32, q->chunk_series & ~31u); /* lane groups of 32 series never straddle chunks */
+    if (q->chunk_series < s->n_series) {
+        /* lane groups are binned inside blocks of OG_IL_SUPER series: chunks that are multiples of it own whole lane groups */
+        if (q->chunk_series >= OG_IL_SUPER) q->chunk_series = q->chunk_series / OG_IL_SUPER * OG_IL_SUPER;
+        else q->chunk_series = std::max<uint32_t>(32, q->chunk_series & ~31u);
+    }
     uint32_t max_chunk_segs = 0;
     for (uint32_t a = 0; a < s->n_series; a += q->chunk_series) {
         uint32_t b = std::min(s->n_series, a + q->chunk_series);
         max_chunk_segs = std::max(max_chunk_segs, s->h_series_seg_begin[b] - s->h_series_seg_begin[a]);
     }
     ChunkP &ch = pl->ch;
-    ch.err = q->d_err;
-    ch.cell_sb = (q->chunk_series + 31) & ~31u;
-    size_t chunk_cells = (size_t)ch.cell_sb * p.n_buckets;
+    ch.err = q->d_err; ch.flags = q->d_err + 2;
+    ch.nb = p.n_buckets;
+    ch.J = ic ? ic->J : 0;
+    size_t chunk_cells = (size_t)std::min(q->chunk_series, s->n_series) * p.n_buckets;
     for (uint32_t c = 0; c < p.n_calls; c++) {
         bool sel = p.calls[c].func >= OG_AGG_MIN;
         if ((rc = salloc(q, &ch.cells[c].val, chunk_cells))) return rc;
@@ -528,45 +589,27 @@ int build_plan(og_query *q) {
         if (sel && (rc = salloc(q, &ch.edges[c].tim, 2 * (size_t)max_chunk_segs))) return rc;
     }
     if ((rc = salloc(q, &ch.edge_bucket, 2 * (size_t)max_chunk_segs))) return rc;
-
-    pl->fused = p.n_cols == 1 && p.n_filter == 0 && !(q->desc.flags & OG_Q_NO_FUSED);
-    q->path_used = pl->fused ? 1 : 0;
-    if (pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments) {
-        /* classify once: which segments the specialised Gorilla kernel takes (the rest go to k_fused_segment) */
-        if ((rc = ensure_il(s, p.col_index[0], st))) return rc;
+    if (pl->fold) { /* folded cell matrix: lane-group columns, then one column per block of 32 consecutive series (stitched edge windows) */
+        ch.gc_edge0 = ic->n_super * ic->cols_per_super; ch.gc_col0 = 0;
+        ch.gc_cols = ch.gc_edge0 + (s->n_series + 31) / 32;
+        const size_t n = (size_t)p.n_buckets * ch.gc_cols;
+        for (uint32_t c = 0; c < p.n_calls; c++) {
+            bool sel = p.calls[c].func >= OG_AGG_MIN;
+            if ((rc = salloc(q, &ch.gcells[c].val, n))) return rc;
+            if ((rc = salloc(q, &ch.gcells[c].ok, n))) return rc;
+            if (sel && (rc = salloc(q, &ch.gcells[c].tim, n))) return rc;
+        }
     }
-    if (pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments && s->il[p.col_index[0]].state == 1) {
-        const og_shard::IlCol &ic = s->il[p.col_index[0]];
-        pl->il.words = ic.words; pl->il.grp_off = ic.grp_off; pl->il.grp_words = ic.grp_words; pl->il.ok = ic.ok; pl->il.lane_seg = ic.lane_seg;
-        pl->il_groups = ic.n_groups; pl->il_J = ic.segs_per_series;
-        if ((rc = salloc(q, &pl->cls, (size_t)s->n_segments))) return rc;
-        k_classify<<<(s->n_segments + 255) / 256, 256, 0, st>>>(make_dir(s), p, ic.ok, pl->cls);
-        CU(cudaGetLastError());
-        /* compact the segments the Gorilla kernel does not take, per class, so that their kernels run with full warps */
-        uint32_t *d_cnt;
-        if ((rc = salloc(q, &d_cnt, 2))) return rc;
-        CU(cudaMemsetAsync(d_cnt, 0, 8, st));
-        for (int k = 0; k < 2; k++) {
-            if ((rc = salloc(q, &pl->cls_list[k], (size_t)s->n_segments))) return rc;
-            k_list_class<<<(s->n_segments + 255) / 256, 256, 0, st>>>(pl->cls, s->n_segments, k == 0 ? (uint8_t)SEG_GENERAL : (uint8_t)SEG_RAW, pl->cls_list[k], d_cnt + k);
-        }
-        uint32_t cnt[2] = {0, 0};
-        CU(cudaMemcpyAsync(cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        for (int k = 0; k < 2; k++) {
-            pl->cls_host[k] = new std::vector<uint32_t>(cnt[k]);
-            if (!cnt[k]) continue;
-            CU(cudaMemcpy(pl->cls_host[k]->data(), pl->cls_list[k], (size_t)cnt[k] * 4, cudaMemcpyDeviceToHost));
-            std::sort(pl->cls_host[k]->begin(), pl->cls_host[k]->end());
-            CU(cudaMemcpy(pl->cls_list[k], pl->cls_host[k]->data(), (size_t)cnt[k] * 4, cudaMemcpyHostToDevice));
-        }
+    if (pl->fast) {
+        pl->il.words = ic->words; pl->il.grp_off = ic->grp_off; pl->il.grp_rows = ic->grp_rows; pl->il.grp_col = ic->grp_col;
+        pl->il.lane_seg = ic->lane_seg; pl->il.lane_rows = ic->lane_rows; pl->il.lane_series = ic->lane_series; pl->il.lane_t0 = ic->lane_t0; pl->il.lane_dt = ic->lane_dt;
         pl->fm = 0; pl->times = false;
         for (uint32_t c = 0; c < p.n_calls; c++) {
             pl->fm |= 1 << (p.calls[c].func - 1);
             if (p.calls[c].func >= OG_AGG_MIN && !(p.multi && p.calls[c].func <= OG_AGG_MAX)) pl->times = true;
         }
         pl->fm |= FM_COUNT; /* the row count also is the validity of every partial */
-        q->path_used = 2;
+        q->path_used = pl->fold ? 3 : 2;
     }
     if (!pl->fused) { /* generic path: materialisation tile */
         TileP &tp = pl->tp;
@@ -611,10 +654,12 @@ OG_API int og_query_run(og_query *q) {
     DirP dir = make_dir(s);
     uint32_t launches = 0, n_chunks = (s->n_series + q->chunk_series - 1) / q->chunk_series;
     while (q->main_ev.size() < 2 * (size_t)n_chunks) { cudaEvent_t e; CU(cudaEventCreate(&e)); q->main_ev.push_back(e); }
-    CU(cudaMemsetAsync(q->d_err, 0, 8, st));
+    CU(cudaMemsetAsync(q->d_err, 0, 16, st));
     CU(cudaEventRecord(q->ev0, st));
     const bool per_series = q->desc.group_mode == OG_GROUP_PER_SERIES;
     if (!per_series) { k_init_dense<<<(unsigned)((cells_dense + 255) / 256), 256, 0, st>>>(p, gp); launches++; } /* per-series: k_merge_per_series writes every cell */
+    /* folded runs touch the per-series cells only on fallback paths: their validity bytes are cleared only after a run that used them */
+    const bool clear_cells = !pl->fold || q->cells_dirty || n_chunks > 1;
     uint64_t segs_scanned = 0; uint32_t ci = 0, chunks_run = 0;
     for (uint32_t a = 0; a < s->n_series; a += q->chunk_series, ci++) {
         if (q->aborted) { cudaStreamSynchronize(st); set_error("query aborted"); return OG_E_ABORTED; }
@@ -622,49 +667,47 @@ OG_API int og_query_run(og_query *q) {
         ch.series_begin = a; ch.series_end = b;
         ch.seg_begin = s->h_series_seg_begin[a]; ch.seg_end = s->h_series_seg_begin[b];
         uint32_t nseg = ch.seg_end - ch.seg_begin;
+        const size_t chunk_cells = (size_t)(b - a) * p.n_buckets;
         if (nseg == 0) {
             if (per_series) { /* series without segments still own dense rows: write them as empty */
-                for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)ch.cell_sb * p.n_buckets, st));
-                k_merge_per_series<<<dim3((p.n_buckets + 31) / 32, (b - a + 31) / 32, p.n_calls), dim3(32, 8), 0, st>>>(p, ch, gp);
+                for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, chunk_cells, st));
+                k_merge_per_series<<<dim3((unsigned)((chunk_cells + 255) / 256), p.n_calls), 256, 0, st>>>(p, ch, gp);
                 launches++;
             }
             continue;
         }
         segs_scanned += nseg;
-        for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, (size_t)ch.cell_sb * p.n_buckets, st));
+        if (clear_cells) for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, chunk_cells, st));
+        /* folded cells are per chunk: a lane group that straddles chunks contributes to its column once per chunk */
+        if (pl->fold) for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.gcells[c].ok, 0, (size_t)p.n_buckets * ch.gc_cols, st));
         CU(cudaEventRecord(q->main_ev[2 * chunks_run], st));
         if (pl->fused) {
-            if (pl->cls) { launch_fast(pl->fm, pl->times, FastArgs{pl->il, pl->il_groups, pl->il_J}, dir, p, ch, pl->cls, st); launches++; }
             const uint32_t *gl = nullptr; uint32_t gn = nseg;
-            if (pl->cls) { /* leftovers of this chunk: a contiguous range of each sorted list */
-                auto range = [&](int k, const uint32_t **l, uint32_t *cnt) {
-                    auto lo = std::lower_bound(pl->cls_host[k]->begin(), pl->cls_host[k]->end(), ch.seg_begin);
-                    auto hi = std::lower_bound(pl->cls_host[k]->begin(), pl->cls_host[k]->end(), ch.seg_end);
-                    *l = pl->cls_list[k] + (lo - pl->cls_host[k]->begin()); *cnt = (uint32_t)(hi - lo);
-                };
-                range(0, &gl, &gn);
-                const uint32_t *rl; uint32_t rn;
-                range(1, &rl, &rn);
-                if (rn) { /* instances by whether min/max need row times and whether a sum is asked for */
-                    const unsigned gb = (rn * 32 + 127) / 128;
-                    const bool need_sum = (pl->fm & FM_SUM) != 0;
-                    if (pl->times) k_fused_raw<63, true><<<gb, 128, 0, st>>>(dir, p, ch, rl, rn);
-                    else if (need_sum) k_fused_raw<FM_SUM | FM_MIN | FM_MAX, false><<<gb, 128, 0, st>>>(dir, p, ch, rl, rn);
-                    else k_fused_raw<FM_MIN | FM_MAX, false><<<gb, 128, 0, st>>>(dir, p, ch, rl, rn);
-                    launches++;
+            if (pl->fast) {
+                const og_shard::IlCol &ic = *pl->ic;
+                /* lane groups of this chunk: those of the blocks of OG_IL_SUPER series it touches (a group that straddles the chunk
+                 * boundary runs in both chunks, with the lanes of each) */
+                uint32_t g0 = 0, g1 = ic.n_groups;
+                if (ic.J) { g0 = ic.super_grp_first[a / OG_IL_SUPER]; g1 = ic.super_grp_first[std::min<uint32_t>(ic.n_super, (b + OG_IL_SUPER - 1) / OG_IL_SUPER)]; }
+                launch_fast(pl->fm, pl->times, pl->fold, pl->il, g0, g1, p, ch, st); launches++;
+                /* leftovers of this chunk: a contiguous range of the sorted list */
+                auto lo = std::lower_bound(ic.gen_host.begin(), ic.gen_host.end(), ch.seg_begin);
+                auto hi = std::lower_bound(ic.gen_host.begin(), ic.gen_host.end(), ch.seg_end);
+                gl = ic.gen_list + (lo - ic.gen_host.begin()); gn = (uint32_t)(hi - lo);
+            }
+            if (gn) {
+                switch (p.n_calls) {
+                case 1: launch_fused<1>(dir, p, ch, gl, gn, st); break;
+                case 2: launch_fused<2>(dir, p, ch, gl, gn, st); break;
+                case 3: launch_fused<3>(dir, p, ch, gl, gn, st); break;
+                case 4: launch_fused<4>(dir, p, ch, gl, gn, st); break;
+                case 5: launch_fused<5>(dir, p, ch, gl, gn, st); break;
+                case 6: launch_fused<6>(dir, p, ch, gl, gn, st); break;
+                case 7: launch_fused<7>(dir, p, ch, gl, gn, st); break;
+                default: launch_fused<8>(dir, p, ch, gl, gn, st); break;
                 }
+                launches++;
             }
-            switch (p.n_calls) {
-            case 1: launch_fused<1>(dir, p, ch, gl, gn, st); break;
-            case 2: launch_fused<2>(dir, p, ch, gl, gn, st); break;
-            case 3: launch_fused<3>(dir, p, ch, gl, gn, st); break;
-            case 4: launch_fused<4>(dir, p, ch, gl, gn, st); break;
-            case 5: launch_fused<5>(dir, p, ch, gl, gn, st); break;
-            case 6: launch_fused<6>(dir, p, ch, gl, gn, st); break;
-            case 7: launch_fused<7>(dir, p, ch, gl, gn, st); break;
-            default: launch_fused<8>(dir, p, ch, gl, gn, st); break;
-            }
-            launches++;
         } else {
             for (uint32_t t0 = ch.seg_begin; t0 < ch.seg_end; t0 += q->tile_segs) {
                 tp.tile_begin = t0; tp.tile_end = std::min(ch.seg_end, t0 + q->tile_segs);
@@ -679,19 +722,19 @@ OG_API int og_query_run(og_query *q) {
         }
         CU(cudaEventRecord(q->main_ev[2 * chunks_run + 1], st));
         chunks_run++;
-        k_fix_edges<<<(nseg + 127) / 128, 128, 0, st>>>(dir, p, ch);
-        bool any_tim = false;
-        for (uint32_t c = 0; c < p.n_calls; c++) any_tim |= gp.dense[c].tim != nullptr;
-        if (per_series) k_merge_per_series<<<dim3((p.n_buckets + 31) / 32, (b - a + 31) / 32, p.n_calls), dim3(32, 8), 0, st>>>(p, ch, gp);
-        else if (q->desc.group_mode == OG_GROUP_ALL && !any_tim) k_merge_all<<<dim3((p.n_buckets + 127) / 128, p.n_calls), 128, 0, st>>>(p, ch, gp);
-        else k_merge_groups<<<dim3((unsigned)((cells_dense + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp);
+        if (pl->fold) k_fix_edges_fold<<<(unsigned)(((size_t)((b - a + 31) / 32) * ch.J * 32 + 127) / 128), 128, 0, st>>>(dir, p, ch);
+        else k_fix_edges<<<(nseg + 127) / 128, 128, 0, st>>>(dir, p, ch);
+        if (per_series) k_merge_per_series<<<dim3((unsigned)((chunk_cells + 255) / 256), p.n_calls), 256, 0, st>>>(p, ch, gp);
+        else k_merge_groups<<<dim3((unsigned)((cells_dense + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp); /* returns at once when no per-series cell was written */
         launches += 2;
+        if (pl->fold) { k_merge_folded<<<dim3((unsigned)(((size_t)p.n_buckets * 32 + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp); launches++; }
     }
     CU(cudaEventRecord(q->ev1, st));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
-    int err[2];
-    CU(cudaMemcpy(err, q->d_err, 8, cudaMemcpyDeviceToHost));
+    int err[4];
+    CU(cudaMemcpy(err, q->d_err, 16, cudaMemcpyDeviceToHost));
+    q->cells_dirty = err[2] != 0;
     if (err[0]) { set_error("segment %d failed to decode (device code %d)", err[1], err[0]); return map_dev_err(err[0]); }
     float ms = 0; cudaEventElapsedTime(&ms, q->ev0, q->ev1);
     double main_ms = 0;
@@ -704,6 +747,12 @@ OG_API int og_query_run(og_query *q) {
     stt.dir_bytes = (uint64_t)segs_scanned * 32; /* SURVEY §8d accounting: 32 B of directory per scanned segment */
     stt.out_bytes = 0;
     for (uint32_t c = 0; c < p.n_calls; c++) stt.out_bytes += cells_dense * (9 + (q->dense[c].tim ? 8 : 0));
+    if (p.n_cols == 1 && p.col_type[0] == OG_TYPE_FLOAT && p.col_index[0] < (int)s->il.size()) {
+        const og_shard::IlCol &ic = s->il[p.col_index[0]];
+        stt.il_state = ic.state; stt.il_build_ms = ic.build_ms; stt.il_bytes = ic.n_words * 4;
+        stt.general_segments = ic.state == 1 ? (uint64_t)ic.gen_host.size() : s->n_segments;
+    }
+    stt.per_series_cells_used = err[2] != 0;
     q->ran = true;
     return OG_OK;
 }

@@ -18,7 +18,7 @@
 
 namespace ogpu {
 
-enum { D_OK = 0, D_UNSUPPORTED = 1, D_CORRUPT = 2, D_TYPE = 3 };
+enum { D_OK = 0, D_UNSUPPORTED = 1, D_CORRUPT = 2, D_TYPE = 3, D_WATCHDOG = 4 /* a device-side progress guard fired (reported as OG_E_CUDA) */ };
 
 /* ---------------- unaligned big-endian loads on top of aligned 64-bit __ldg ---------------- */
 __device__ __forceinline__ uint64_t bswap64(uint64_t v) {

@@ -62,9 +62,8 @@ struct FusedState {
 #pragma unroll
             for (int c = 0; c < NC; c++) store_part(ch.edges[c], e + 1, parts[c]);
         } else {
-            size_t ci = cell_idx(ch, series, cur_b);
 #pragma unroll
-            for (int c = 0; c < NC; c++) if (parts[c].ok) store_part(ch.cells[c], ci, parts[c]);
+            for (int c = 0; c < NC; c++) if (parts[c].ok) store_cell(ch, c, series, cur_b, parts[c]);
         }
     }
     __device__ __forceinline__ void row_step(bool valid, uint64_t bits) {

@@ -50,10 +50,13 @@ struct og_shard {
     void *h_seg_buf = nullptr; size_t h_seg_buf_bytes = 0;
     void *d_seg_buf = nullptr; size_t d_seg_buf_bytes = 0;
     std::vector<og_colval_view> seg_views;
-    /* lane-interleaved stream copy per column for the fast Gorilla kernel (fused_fast.cuh), built on first use */
-    struct IlCol { int state = 0; /* 0 not built, 1 ready, -1 unavailable (no eligible segment / out of memory) */
-                   uint32_t *words = nullptr; uint64_t *grp_off = nullptr; uint32_t *grp_words = nullptr; uint8_t *ok = nullptr;
-                   uint32_t *lane_seg = nullptr; uint32_t n_groups = 0, segs_per_series = 0; /* segs_per_series != 0: lanes = 32 consecutive series */
+    /* lane-interleaved, length-binned stream copy per column for the fused Gorilla kernel (fused_il.cuh), built on first use */
+    struct IlCol { int state = 0; /* 0 not built, 1 ready, -1 no eligible segment, -2 not enough device memory (general kernel serves the column) */
+                   uint32_t *words = nullptr; uint64_t *grp_off = nullptr; uint32_t *grp_rows = nullptr, *grp_col = nullptr; uint8_t *ok = nullptr;
+                   uint32_t *lane_seg = nullptr, *lane_rows = nullptr, *lane_series = nullptr; int64_t *lane_t0 = nullptr; uint64_t *lane_dt = nullptr;
+                   uint32_t *gen_list = nullptr; std::vector<uint32_t> gen_host; /* segments the fused kernel does not take (ascending), device + host */
+                   uint32_t n_groups = 0, J = 0; /* J != 0: regular shard, lane groups share a segment index */
+                   uint32_t n_super = 1, cols_per_super = 0; std::vector<uint32_t> super_grp_first; /* [n_super+1] first lane group of each block of OG_IL_SUPER series */
                    uint64_t n_words = 0; double build_ms = 0; };
     std::vector<IlCol> il; /* [n_columns] */
     std::mutex il_mu;      /* queries of one shard may be planned from different threads: the build is serialised */
@@ -109,7 +112,8 @@ struct og_query {
     std::vector<std::vector<int64_t>> rv_coltimes;
     std::vector<int64_t> rv_times;
     std::vector<og_colval_view> rv_cols;
-    int path_used = 0; /* 0 generic tile path, 1 fused */
+    int path_used = 0; /* 0 generic tile path, 1 fused (general kernel), 2 fused Gorilla kernel, per-series cells, 3 fused Gorilla kernel, folded cells */
+    bool cells_dirty = true; /* per-series cell validity bytes need clearing before the next run */
     /* execution plan + scratch, built by the first og_query_run and reused by later runs */
     bool planned = false;
     uint32_t chunk_series = 0, tile_segs = 0;

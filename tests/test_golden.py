@@ -114,7 +114,8 @@ def test_gpu_reproduces_golden_aggregates():
     for qn in [str(x) for x in SHARD["query_names"]]:
         calls = [(names[int(f)], int(c)) for f, c in SHARD[f"q/{qn}/calls"]]
         ivl, tmin, tmax, gm, ng, nb, start = (int(v) for v in SHARD[f"q/{qn}/params"])
-        q = AggQuery(sh, calls, ivl, tmin, tmax, group={L.GROUP_ALL: "all", L.GROUP_PER_SERIES: "series"}[gm]).run()
+        # the fixtures hold the reference's summation order: OG_Q_STRICT_ORDER (the default one-tagset order folds 32 series first)
+        q = AggQuery(sh, calls, ivl, tmin, tmax, group={L.GROUP_ALL: "all", L.GROUP_PER_SERIES: "series"}[gm], flags=L.Q_STRICT_ORDER).run()
         got = q.dense_host()
         assert (got["n_groups"], got["n_buckets"], got["start"]) == (ng, nb, start)
         for k in range(len(calls)):
