@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libogpu.so")
+LIB_PATH = os.environ.get("OGPU_LIB") or os.path.join(_HERE, "libogpu.so")  # OGPU_LIB: A/B builds of the same library (tools/)
 
 # ---- status codes / enums (mirror include/ogpu.h) ----
 OG_OK, OG_EOF = 0, 1

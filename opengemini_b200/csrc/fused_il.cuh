@@ -64,9 +64,11 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
 enum { FM_COUNT = 1, FM_SUM = 2, FM_MIN = 4, FM_MAX = 8, FM_FIRST = 16, FM_LAST = 32 };
 enum { SEG_GENERAL = 0, SEG_FAST = 1, SEG_RAWX = 2 }; /* static per-segment classes (k_il_scan): general kernel / Gorilla stream / raw page transcoded to XOR deltas */
 
+#ifndef OG_FAST_THREADS
 #define OG_FAST_THREADS 128
-#ifndef OG_FAST_MINB
-#define OG_FAST_MINB 4
+#endif
+#ifndef OG_FAST_MAXREG
+#define OG_FAST_MAXREG 80 /* registers are granted in steps of 8 per thread: 80 lets six 128-thread blocks share an SM, 88 only five */
 #endif
 #ifndef OG_IL_NW
 #define OG_IL_NW 64u            /* ring rows (words per lane resident) */
@@ -137,12 +139,12 @@ __device__ __forceinline__ Part fold32(int func, int type, bool multi, Part p, b
     return warp_fold(func, type, multi, p, with_time);
 }
 
-#define OG_IL_WCAP 32u /* windows of one segment a folding warp accumulates in shared memory; segments that span more run unfolded */
+#define OG_IL_WCAP 24u /* windows of one segment a folding warp accumulates in shared memory; segments that span more run unfolded */
 /* dynamic shared memory per warp for the window accumulators of a folding warp: n_calls x WCAP x {u64 value, i64 time, u8 valid} */
 __host__ __device__ inline uint32_t il_acc_bytes(uint32_t n_calls, bool times) { return OG_IL_WCAP * n_calls * (times ? 17u : 9u) + 8u & ~7u; }
 
 template <int FM, bool TIMES, bool FOLD>
-__global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_il(QueryP q, ChunkP ch, IlP il, uint32_t grp_begin, uint32_t grp_end) {
+__global__ void __maxnreg__(OG_FAST_MAXREG) k_fused_il(QueryP q, ChunkP ch, IlP il, uint32_t grp_begin, uint32_t grp_end) {
     constexpr uint32_t NW = OG_IL_NW, B = OG_IL_B, NB = OG_IL_NB, K = OG_IL_K;
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr uint32_t WPB = OG_FAST_THREADS / 32;
@@ -195,16 +197,26 @@ __global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_il(Quer
     const uint32_t *gsrc = il.words + goff;
     uint32_t issued_b = 0, ready_b = 0; /* warp-uniform: batches issued / known complete */
     uint32_t hung = 0;                  /* warp-uniform watchdog code: 1 a batch never landed, 2 the round limit was hit */
-    auto issue = [&](uint32_t k) { /* lane 0 only */
+    /* every lane calls issue(); one elected lane performs it.  The batch index goes through a warp reduction so that slot, ring,
+     * barrier and source addresses are uniform-register arithmetic (the bulk copy takes uniform operands; per-thread values would
+     * make the compiler wrap it in a broadcast loop) */
+    auto issue = [&](uint32_t k_any) {
+        const uint32_t k = __reduce_max_sync(FULL, k_any);
         const uint32_t s = k % NB, dst = win + s * (B * 128), bar = bar0 + s * 8;
         const uint32_t *src = gsrc + (size_t)k * (B * 32);
-        if (s == 0) { mbar_expect_tx(bar, B * 128 + 256u); bulk_g2s(win + NW * 128, src, 256, bar); } /* + mirror rows */
-        else mbar_expect_tx(bar, B * 128);
-        bulk_g2s(dst, src, B * 128, bar);
+        if (s == 0) /* slot 0 also refreshes the two mirror rows behind the ring */
+            asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\n@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                         "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %4, [%0];\n"
+                         "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%3], 256, [%0];\n}"
+                         ::"r"(bar), "r"(B * 128 + 256u), "r"(dst), "l"(src), "r"(B * 128), "r"(win + NW * 128) : "memory");
+        else
+            asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\n@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                         "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n}"
+                         ::"r"(bar), "r"(B * 128), "r"(dst), "l"(src) : "memory");
     };
     {
         const uint32_t first = total_b < NB ? total_b : NB;
-        if (lane == 0) for (uint32_t k = 0; k < first; k++) issue(k);
+        for (uint32_t k = 0; k < first; k++) issue(k);
         issued_b = first;
     }
 
@@ -384,39 +396,60 @@ __global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_il(Quer
         /* next record */
         const uint64_t x = fetch64(col, qp);
         const bool slow = (((uint32_t)(x >> 32) & CM) ^ CE) != 0;
-        if (!slow) { val ^= x & MASK; qp += kfast; } /* '10' with the window in place, raw delta, or an idle lane */
-        else slow_record();
+        if (__builtin_expect(slow, 0)) slow_record(); /* kept out of the straight-line path */
+        else { val ^= x & MASK; qp += kfast; } /* '10' with the window in place, raw delta, or an idle lane */
     };
 
-    /* every round the slowest live lane decodes K records, so 32 lanes finish within 32 * (rows / K + 1) rounds plus the skipped prefix */
+    /* Rounds.  Every round the slowest live lane decodes K records, so 32 lanes finish within 32 * (rows / K + 1) eventful rounds.
+     * The common round — every lane resident, no window boundary within K records — costs two warp reductions and a handful of
+     * uniform compares on top of the K records; everything else (events, lanes that drifted ahead of the ring) is the rare path. */
     uint32_t rounds_left = hung ? 0u : 40u * (__reduce_max_sync(FULL, rows) / K + 8u);
+#ifdef OG_IL_STATS
+    uint32_t st_common = 0, st_rare = 0, st_sit = 0, st_notgo = 0;
+#endif
     for (;;) {
-        /* ---- service: ring refill, residency, who runs this round ---- */
-        if (rounds_left-- == 0) { if (!hung) hung = 2; break; }
         const uint32_t qmin = __reduce_min_sync(FULL, done ? 0xffffffffu : qp);
         if (qmin == 0xffffffffu) break; /* every lane is finished */
-        if (!done && (qp >> 5) >= rows_w) { bad = 1; retire(); } /* ran past the stream: corrupt page */
-        const uint32_t qmax = __reduce_max_sync(FULL, done ? 0u : qp);
         const uint32_t f = qmin < 32 ? 0u : (qmin - 32) >> 5; /* rows below f are dead (q may step back by < 32 bits when a window changes) */
 #pragma unroll 1
-        while (issued_b < total_b && (issued_b + 1) * B <= f + NW) { if (lane == 0) issue(issued_b); issued_b++; }
+        while (issued_b < total_b && (issued_b + 1) * B <= f + NW) { issue(issued_b); issued_b++; }
+        /* the rows the lanes may touch this round must have landed; batches beyond the most advanced lane's look-ahead stay in
+         * flight (they were issued when the ring had room, about two rounds before they are needed) */
+        const uint32_t qmax = __reduce_max_sync(FULL, done ? 0u : qp);
         uint32_t need_max = ((qmax + OG_IL_LOOKBITS) >> 5) + 1; if (need_max > rows_w) need_max = rows_w;
         uint32_t want_b = (need_max + B - 1) / B; if (want_b > issued_b) want_b = issued_b;
 #pragma unroll 1
         while (ready_b < want_b) { if (!mbar_wait(bar0 + (ready_b % NB) * 8, (ready_b / NB) & 1)) { hung = 1; break; } ready_b++; }
         if (hung) break;
         uint32_t need = ((qp + OG_IL_LOOKBITS) >> 5) + 1; if (need > rows_w) need = rows_w;
-        const bool go = done || need <= ready_b * B; /* a lane that could touch rows not resident yet sits the round out */
-        const bool all_go = __all_sync(FULL, go);
-        /* ---- K records per running lane, in runs that end where the first lane reaches a window boundary.  Lanes of a binned
-         * group move in lockstep, so most rounds are one unchecked run of K records (6.5 rounds of 7.5 at 60 rows per window). ---- */
+        bool go = done || need <= ready_b * B; /* a lane that could touch rows not resident yet sits the round out */
+        uint32_t run = __reduce_min_sync(FULL, go ? n_ev : 0u); /* finished lanes have n_ev near 2^32 */
+        if (run >= K) { /* every lane runs, no boundary ahead */
+#pragma unroll
+            for (uint32_t k = 0; k < K; k++) record(k);
+            n_ev -= K;
+#ifdef OG_IL_STATS
+            st_common++;
+#endif
+            continue;
+        }
+#ifdef OG_IL_STATS
+        st_rare++;
+#endif
+        /* ---- the rare round ---- */
+        if (rounds_left-- == 0) { hung = 2; break; }
+        const bool all_go = __all_sync(FULL, go); /* false: some lane is so far ahead of the slowest one that the ring cannot hold both */
+#ifdef OG_IL_STATS
+        if (!all_go) { st_notgo++; st_sit += __popc(__ballot_sync(FULL, !go)); }
+#endif
+        /* K records per running lane, in runs that end where the first lane reaches a window boundary */
         uint32_t left = K;
         for (;;) {
-            uint32_t run = __reduce_min_sync(FULL, go ? n_ev : 0xffffffffu); /* finished lanes have n_ev near 2^32 */
+            run = __reduce_min_sync(FULL, go ? n_ev : 0xffffffffu);
             if (run > left) run = left;
-            if (run == K && all_go) {
-#pragma unroll
-                for (uint32_t k = 0; k < K; k++) record(k);
+            if (all_go) {
+#pragma unroll 1
+                for (uint32_t k = 0; k < run; k++) record(k);
             } else {
 #pragma unroll 1
                 for (uint32_t k = 0; k < run; k++) if (go) record(k);
@@ -434,6 +467,10 @@ __global__ void __launch_bounds__(OG_FAST_THREADS, OG_FAST_MINB) k_fused_il(Quer
             if (ev) advance();
         }
     }
+    if (active && (qp >> 5) >= rows_w) bad = 1; /* ran past the stream: corrupt page */
+#ifdef OG_IL_STATS
+    if (lane == 0) { atomicAdd((unsigned *)&ch.err[4], st_common); atomicAdd((unsigned *)&ch.err[5], st_rare); atomicAdd((unsigned *)&ch.err[6], st_notgo); atomicAdd((unsigned *)&ch.err[7], st_sit); }
+#endif
     /* copies still in flight must land before this CTA's shared memory can be reused */
     while (ready_b < issued_b && hung != 1) { if (!mbar_wait(bar0 + (ready_b % NB) * 8, (ready_b / NB) & 1)) hung = 1; ready_b++; }
     if (hung && lane == 0) report_err(ch.err, D_WATCHDOG, (grp << 2) | hung);
