@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-series", type=int, default=0, help="series of the CPU sample (0 = auto: 4 per host thread)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the answer check after the timed loop")
+    ap.add_argument("--verify-series", type=int, default=4, help="series sampled for the bitwise check against the oracle")
     return ap.parse_args()
 
 
@@ -108,7 +110,7 @@ def ncu_traffic(a):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
     (profiles/traffic.json); only valid for the workload it was captured on, else null."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_fused_fast"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_fused_il"]
         if a.series == 10000 and a.rows == 1000000 and a.dist == "hi":
             return t["dram_bytes_per_launch"]
     except Exception:
@@ -217,16 +219,119 @@ def run_reference(a):
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
-def cross_shard_merge(torch, dist, q, dense, world):
-    """configs[3]: NCCL merge of the dense bucket arrays (opengemini_b200/shard_merge.py)."""
-    from opengemini_b200 import shard_merge
-    shard_merge.cross_shard_merge(torch, dist, dense["cols"], world, shard_merge.gpu_fold(torch, q))
+class VerifyError(RuntimeError):
+    pass
+
+
+def verify_answer(a, L, sh, q, calls, tmax, rank, info):
+    """The timed query's answer, checked at full size (the run fails with rc != 0 on a mismatch):
+    (1) sum of the per-bucket counts == rows of the shard;
+    (2) the folded (default) sums against the strict-order run of the same query: <= 1e-12 relative; counts and max bitwise;
+    (3) K sampled series, aggregated on the GPU through a tag-group map (strict per-series order), bitwise against the CPU
+        oracle's scan of the same series rebuilt from the same seed (og_synth_desc.series_base)."""
+    import numpy as np
+    import oracle
+    from opengemini_b200 import AggQuery
+    t0 = time.perf_counter()
+    q.run()  # this shard's own answer (at N > 1 the timed steps left the cross-shard merge in the dense arrays)
+    d = q.dense_host()
+    cnt = d["cols"][1]["values"].astype(np.int64) * d["cols"][1]["valid"]
+    if int(cnt.sum()) != int(info["n_rows"]):
+        raise VerifyError(f"sum of bucket counts {int(cnt.sum())} != rows {info['n_rows']}")
+    qs = AggQuery(sh, calls, 60 * SEC, T0, tmax, flags=L.Q_STRICT_ORDER).run()
+    ds = qs.dense_host()
+    qs.close()
+    for k, name in enumerate(("sum", "count", "max")):
+        if not np.array_equal(d["cols"][k]["valid"], ds["cols"][k]["valid"]):
+            raise VerifyError(f"{name}: validity of the folded and the strict-order run differ")
+        m = ds["cols"][k]["valid"].astype(bool)
+        if name == "sum":
+            rel = np.abs(d["cols"][k]["values"][m] - ds["cols"][k]["values"][m]) / np.abs(ds["cols"][k]["values"][m])
+            if rel.size and rel.max() > 1e-12:
+                raise VerifyError(f"folded sums differ from strict-order sums by {rel.max():.3e} relative")
+            max_rel = float(rel.max()) if rel.size else 0.0
+        elif not np.array_equal(d["cols"][k]["values"].view(np.uint64)[m], ds["cols"][k]["values"].view(np.uint64)[m]):
+            raise VerifyError(f"{name}: folded and strict-order runs differ")
+    K = max(0, min(a.verify_series, a.series))
+    rng = np.random.default_rng(12345 + rank)
+    picks = sorted(set(int(x) for x in rng.integers(0, a.series, K))) if K else []
+    if picks:
+        grp = np.zeros(a.series, np.uint32)
+        for i, s_ in enumerate(picks):
+            grp[s_] = i + 1
+        qm = AggQuery(sh, calls, 60 * SEC, T0, tmax, group="map", series_group=grp, n_groups=len(picks) + 1).run()
+        dm = qm.dense_host()
+        nb = dm["n_buckets"]
+        for i, s_ in enumerate(picks):
+            hs = oracle.HostShard(1, a.rows, [(L.TYPE_FLOAT, dist_const(L, a), 0)], t0=T0, dt=SEC, seed=1000 + rank, series_base=s_)
+            ref = oracle.scan(hs.desc, q.desc, threads=1)
+            for k, name in enumerate(("sum", "count", "max")):
+                gv = dm["cols"][k]["valid"][(i + 1) * nb:(i + 2) * nb].astype(bool)
+                gb = dm["cols"][k]["values"].view(np.uint64)[(i + 1) * nb:(i + 2) * nb]
+                rv = ref["cols"][k]["valid"].astype(bool)
+                if not np.array_equal(gv, rv) or not np.array_equal(gb[rv], ref["cols"][k]["values"][rv]):
+                    raise VerifyError(f"series {s_}: {name} differs from the oracle (bitwise)")
+        qm.close()
+    return {"rows_counted": int(cnt.sum()), "folded_vs_strict_sum_max_rel": max_rel, "series_checked_bitwise_vs_oracle": picks,
+            "seconds": round(time.perf_counter() - t0, 2)}
+
+def make_comm(torch, dist, Comm, rank, world, dev):
+    """The library's own NCCL communicator (og_comm_*): rank 0's 128-byte id travels over torch.distributed (plumbing only);
+    the merge itself is og_query_allreduce inside libogpu.so."""
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, src=0)
+    return Comm.init_rank(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+
+def verify_merge(a, L, comm, rank, world):
+    """configs[3] answer check at N > 1: every rank builds a SMALL shard (own seed), runs the bench query and the library's
+    NCCL merge; the merged record (identical on every rank) is compared with the oracle's scans of the same shards merged on the
+    host with the reference's rules (sum/count add, max = larger).  Sums 1e-9 relative, counts and max exact."""
+    import numpy as np
+    import oracle
+    from opengemini_b200 import AggQuery, Shard
+    ns, rows = 64, 20_000
+    cols = [(L.TYPE_FLOAT, dist_const(L, a), 0)]
+    calls = [("sum", 0), ("count", 0), ("max", 0)]
+    sh = Shard.synth(ns, rows, cols, t0=T0, dt=SEC, seed=7000 + rank)
+    q = AggQuery(sh, calls, 60 * SEC, T0, T0 + (rows - 1) * SEC, flags=L.Q_QUERY_GRID).run()
+    comm.allreduce(q)
+    got = q.dense_host()
+    exp = None
+    for r in range(world):
+        hs = oracle.HostShard(ns, rows, cols, t0=T0, dt=SEC, seed=7000 + r)
+        ref = oracle.scan(hs.desc, q.desc, threads=1)
+        part = [(c["values"].copy(), c["valid"].astype(bool)) for c in ref["cols"]]
+        if exp is None:
+            exp = part
+            continue
+        (s0, k0), (c0, kc0), (m0, km0) = exp
+        (s1, k1), (c1, kc1), (m1, km1) = part
+        ssum = np.where(k0, s0.view(np.float64), 0.0) + np.where(k1, s1.view(np.float64), 0.0)
+        cnt = np.where(kc0, c0.view(np.int64), 0) + np.where(kc1, c1.view(np.int64), 0)
+        mx = np.where(km0 & km1, np.maximum(m0.view(np.float64), m1.view(np.float64)), np.where(km0, m0.view(np.float64), m1.view(np.float64)))
+        exp = [(ssum.view(np.uint64), k0 | k1), (cnt.view(np.uint64), kc0 | kc1), (mx.view(np.uint64), km0 | km1)]
+    for k, name in enumerate(("sum", "count", "max")):
+        ev, ek = exp[k]
+        if not np.array_equal(got["cols"][k]["valid"].astype(bool), ek):
+            raise VerifyError(f"merged {name}: validity differs from the oracle")
+        g = got["cols"][k]["values"]
+        if name == "sum":
+            rel = np.abs(g[ek] - ev.view(np.float64)[ek]) / np.abs(ev.view(np.float64)[ek])
+            if rel.max() > 1e-9:
+                raise VerifyError(f"merged sums off by {rel.max():.3e} relative")
+        elif not np.array_equal(g.view(np.uint64)[ek], ev[ek]):
+            raise VerifyError(f"merged {name} differs from the oracle")
+    q.close(); sh.close()
+    return {"shards": world, "series_per_shard": ns, "rows_per_series": rows, "checked": "sum<=1e-9 rel, count and max exact vs the oracle on the same shards"}
 
 
 def run_ours(a):
     import numpy as np
     import torch
-    from opengemini_b200 import AggQuery, Shard
+    from opengemini_b200 import AggQuery, Comm, Shard
     from opengemini_b200 import _lib as L
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -259,19 +364,19 @@ def run_ours(a):
     info = sh.info()
     calls = [("sum", 0), ("count", 0), ("max", 0)]
     tmax = T0 + (a.rows - 1) * SEC
-    q = AggQuery(sh, calls, 60 * SEC, T0, tmax)
+    comm = make_comm(torch, dist, Comm, rank, world, dev) if world > 1 else None
+    q = AggQuery(sh, calls, 60 * SEC, T0, tmax, flags=L.Q_QUERY_GRID if world > 1 else 0)
+    merge_ms_total = [0.0]
 
     def step():
         q.run()
         st = q.stats()
         ms = st["kernel_ms"]
-        if world > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            cross_shard_merge(torch, dist, q, q.dense(dev), world)
-            e1.record()
-            torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
+        if comm is not None:  # cross-shard merge inside libogpu.so (NCCL all-reduce + all-gather/fold, one CUDA graph); CUDA events on the query stream
+            comm.allreduce(q)
+            m = q.stats()["merge_ms"]
+            ms += m
+            merge_ms_total[0] += m
         return ms, st
 
     for _ in range(max(a.warmup, 3)):
@@ -302,15 +407,25 @@ def run_ours(a):
     total_rows = rows_t.item()
     value = total_rows * a.steps / (dev_ms_max / 1e3)
 
-    # roofline of the dominant kernel (k_fused_fast): algorithmic bytes per launch / its average duration
+    verify = verify_answer(a, L, sh, q, calls, tmax, rank, info) if not a.no_verify else None
+    if comm is not None and not a.no_verify:
+        vm = verify_merge(a, L, comm, rank, world)
+        if verify is not None:
+            verify["cross_shard_merge"] = vm
+
+    # roofline of the dominant kernel: algorithmic bytes per launch / its average duration
     peak, peak_src = measured_peak()
-    algo_bytes = st["page_bytes"] + st["dir_bytes"] + 16667 * 3 * 8  # pages + 32 B/segment directory + dense output
+    algo_bytes = st["page_bytes"] + st["dir_bytes"] + st["out_bytes"]  # pages + 32 B/segment directory + dense output (og_stats)
     main_per_launch_ms = main_ms / a.steps
     achieved = algo_bytes / (main_per_launch_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_fused_fast<SUM|COUNT|MAX>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    kernel_name = {3: "k_fused_il<SUM|COUNT|MAX, fold> (+ k_fused_segment for %d general segments)" % st["general_segments"],
+                   2: "k_fused_il<SUM|COUNT|MAX> (+ k_fused_segment)", 1: "k_fused_segment", 0: "k_decode_tile+k_filter_tile+k_window_reduce"}[st["path"]]
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(a), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "bytes_per_row": algo_bytes / max(1, st["rows_decoded"]), "kernel_ms": main_per_launch_ms,
-                "share_of_step": main_ms / max(1e-9, dev_ms if world == 1 else main_ms)}
+                "share_of_step": main_ms / max(1e-9, dev_ms if world == 1 else main_ms),
+                "interleaved_copy": {"build_ms_once_per_shard": st["il_build_ms"], "bytes": st["il_bytes"], "state": st["il_state"],
+                                     "note": "built by the first query on the column (inside warm-up here, inside the timed region of the e2e leg)"}}
 
     # e2e: the call a user of the C ABI makes, with HOST buffers (pinned), H2D + query + D2H in the timed region
     e2e = None
@@ -373,7 +488,7 @@ def run_ours(a):
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         e_rows = ns * a.rows * world
         # d2h: the three dense columns (value + validity) are copied back whole before records are sliced
-        d2h_full = 16667 * 3 * 9
+        d2h_full = int(st["out_bytes"])
         e2e = {"value": e_rows * e_steps / et.item(), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": max(d2h, d2h_full),
                "sample": f"{ns} series x {a.rows} rows per GPU per step (host-resident, pinned), og_shard_open + og_query_run + og_query_next",
                "steps": e_steps, "phase_ms_per_step": {k: round(v / e_steps, 2) for k, v in phases.items()}, "ms_per_step": et.item() / e_steps * 1e3, "out_rows": out_rows}
@@ -410,12 +525,15 @@ def run_ours(a):
                 "config": {"workload": workload_name(a), "shards": world, "rows_per_shard": int(info["n_rows"]), "segments_per_shard": int(info["n_segments"]),
                            "page_bytes_per_shard": int(info["page_bytes"]), "compressed_bytes_per_value": info["page_bytes"] / max(1, info["n_rows"]),
                            "l2": "inputs (tens of GB per step) are far larger than the 126 MB L2; no explicit flush",
-                           "parallelism": f"shard-per-gpu x{world}" + (", NCCL all-reduce(sum,count) + all-gather/fold(max)" if world > 1 else ""),
-                           "timing": "CUDA events on the query stream (og_stats.kernel_ms) + torch events around the NCCL merge; max over ranks",
+                           "parallelism": f"shard-per-gpu x{world}" + (", og_query_allreduce: NCCL all-reduce(sum,count) + all-gather/fold(max) inside libogpu.so" if world > 1 else ""),
+                           "timing": "CUDA events on the query stream (og_stats.kernel_ms + og_stats.merge_ms); max over ranks",
+                           "merge_ms_per_step": merge_ms_total[0] / (max(a.warmup, 3) + a.steps) if world > 1 else 0.0,
                            "synth_seconds": gen_s},
-                "wall_ms_per_step": wall_ms_max / a.steps, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "wall_ms_per_step": wall_ms_max / a.steps, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "verify": verify,
                 "gpu_launches": launches + e2e_launches}
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

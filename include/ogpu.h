@@ -98,6 +98,11 @@ enum {
     OG_Q_NO_FAST = 1u << 2 /* fused path, but without the specialised Gorilla/const-delta kernel (testing / A-B) */
     ,
     OG_Q_RESERVED_8 = 1u << 3 /* was an A/B switch of the round-1 staging experiments; ignored */
+    ,
+    OG_Q_QUERY_GRID = 1u << 4 /* lay the dense interval record over the QUERY range [tmin, tmax] instead of its intersection with the
+                                 shard's own time range (FileInfo.MinTime/MaxTime).  Every shard of a cross-shard query then builds the
+                                 same (start, interval, n_buckets) grid, which og_query_merge_dense / og_query_allreduce require; the
+                                 range must be bounded (not MinTime/MaxTime) */
 };
 
 typedef struct og_query_desc {
@@ -207,6 +212,7 @@ typedef struct og_stats {
     double il_build_ms;        /* one-off cost of building that copy (first query on the column) */
     uint64_t il_bytes;         /* its size in HBM */
     uint64_t general_segments; /* segments of the column that the Gorilla kernel does not take (other codecs, nulls, irregular time pages) */
+    double merge_ms;           /* device time of the last og_query_allreduce (pack + collectives + fold) */
 } og_stats;
 
 typedef struct og_shard og_shard;
@@ -239,6 +245,21 @@ OG_API void og_query_destroy(og_query *q);
  * (lib/record/reccord_functions.go:482-494).  `other` holds device pointers laid out like og_query_dense's. */
 OG_API int og_query_merge_dense(og_query *q, const og_dense_view *other);
 
+/* ---- cross-shard merge over NCCL (one shard per GPU, one process per GPU) ----
+ * Replaces the exchange of per-shard partial aggregates between store and sql nodes (engine/executor/rpc_transform.go:40-282,
+ * agg_transform.go:248-304).  Rank 0 makes an id with og_comm_unique_id and hands the 128 bytes to the other ranks through any
+ * channel the host already has; every rank then calls og_comm_init_rank (collective).  og_query_allreduce (collective, same
+ * query descriptor with OG_Q_QUERY_GRID on every rank) leaves the merged dense interval record on every rank: sums and counts
+ * by ncclAllReduce, min/max/first/last by ncclAllGather + a fold in rank order with the reference's tie-breaks
+ * (lib/record/reccord_functions.go:482-494).  NCCL is loaded with dlopen("libnccl.so.2") (override: OGPU_NCCL_LIB). */
+typedef struct og_comm og_comm;
+OG_API int og_comm_unique_id(uint8_t id[128]);
+OG_API int og_comm_init_rank(const uint8_t id[128], int rank, int world, og_comm **out);
+OG_API void og_comm_destroy(og_comm *c);
+OG_API int og_comm_info(const og_comm *c, int *rank, int *world, int *nccl_version);
+OG_API int og_comm_allreduce_f64(og_comm *c, double *vals, int n, int op_max); /* small host-side reduction (sum, or max when op_max) */
+OG_API int og_query_allreduce(og_query *q, og_comm *c);
+
 /* ---- materialise path (KeyCursor.Next for non-aggregating callers) ---- */
 OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out);
 /* decode a range of segments of one column into caller-provided DEVICE buffers (dense values, 8 B or 1 B each);
@@ -262,6 +283,9 @@ typedef struct og_synth_desc {
     uint64_t seed;
     uint32_t n_columns;
     const og_synth_column *columns;
+    uint32_t series_base;      /* the shard holds series [series_base, series_base + n_series) of the synthetic population: the values
+                                  of a series depend on (seed, column, series, row) only, so a small shard can reproduce any series
+                                  of a large one (bench.py checks sampled series of the 10^10-row shard against the oracle this way) */
 } og_synth_desc;
 OG_API int og_shard_synth(const og_synth_desc *desc, og_shard **out);
 /* copy a shard's pages + directory back to host (for parity tests against the oracle): caller passes buffers

@@ -4,6 +4,6 @@ Product = libogpu.so (hand-written sm_100a CUDA behind the C ABI in include/ogpu
 This package only holds the host-side bindings; it never computes on the CPU.
 """
 from . import _lib  # noqa: F401
-from .cursor import AggQuery, Shard  # noqa: F401
+from .cursor import AggQuery, Comm, Shard  # noqa: F401
 
-__all__ = ["Shard", "AggQuery", "_lib"]
+__all__ = ["Shard", "AggQuery", "Comm", "_lib"]

@@ -20,6 +20,7 @@ GROUP_ALL, GROUP_PER_SERIES, GROUP_MAP = 0, 1, 2
 Q_STRICT_ORDER = 1
 Q_NO_FUSED = 2
 Q_NO_FAST = 4
+Q_QUERY_GRID = 16
 SYNTH_F_HI, SYNTH_F_LO, SYNTH_INT_WALK, SYNTH_BOOL = 0, 1, 2, 3
 SHARD_DEVICE_DATA = 1
 
@@ -76,7 +77,7 @@ class Stats(C.Structure):
     _fields_ = [("rows_decoded", C.c_uint64), ("segments_scanned", C.c_uint64), ("page_bytes", C.c_uint64),
                 ("dir_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("main_kernel_ms", C.c_double),
                 ("kernel_launches", C.c_uint32), ("path", C.c_int32), ("il_state", C.c_int32), ("per_series_cells_used", C.c_int32),
-                ("il_build_ms", C.c_double), ("il_bytes", C.c_uint64), ("general_segments", C.c_uint64)]
+                ("il_build_ms", C.c_double), ("il_bytes", C.c_uint64), ("general_segments", C.c_uint64), ("merge_ms", C.c_double)]
 
 
 class SynthColumn(C.Structure):
@@ -86,7 +87,7 @@ class SynthColumn(C.Structure):
 class SynthDesc(C.Structure):
     _fields_ = [("n_series", C.c_uint32), ("rows_per_series", C.c_uint32), ("rows_per_segment", C.c_uint32),
                 ("t0", C.c_int64), ("dt", C.c_int64), ("seed", C.c_uint64), ("n_columns", C.c_uint32),
-                ("columns", C.POINTER(SynthColumn))]
+                ("columns", C.POINTER(SynthColumn)), ("series_base", C.c_uint32)]
 
 
 class ShardLayout(C.Structure):
@@ -99,6 +100,7 @@ EXPORTS = [
     "og_shard_info", "og_query_create", "og_query_run", "og_query_next", "og_query_dense", "og_query_stats",
     "og_query_abort", "og_query_destroy", "og_query_merge_dense", "og_decode_segment", "og_decode_column_device",
     "og_shard_synth", "og_shard_layout_get", "og_shard_export", "og_encode_pages",
+    "og_comm_unique_id", "og_comm_init_rank", "og_comm_destroy", "og_comm_info", "og_comm_allreduce_f64", "og_query_allreduce",
 ]
 
 _lib = None
@@ -146,6 +148,13 @@ def lib():
     L.og_shard_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.og_encode_pages.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, u64p]
+    L.og_comm_unique_id.argtypes = [C.c_void_p]
+    L.og_comm_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.og_comm_destroy.argtypes = [C.c_void_p]
+    L.og_comm_destroy.restype = None
+    L.og_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.og_comm_allreduce_f64.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int]
+    L.og_query_allreduce.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

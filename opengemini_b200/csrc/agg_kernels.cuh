@@ -71,6 +71,9 @@ __device__ __forceinline__ void store_cell(const ChunkP &ch, int call, uint32_t 
 /* ------------------------------------------------------------------------------------------------------------
  * shard open: row counts, codec support and framing validation (one thread per segment)
  * ------------------------------------------------------------------------------------------------------------ */
+/* last time of a page and whether its times ascend (segments hold time-ordered rows, lib/record/record.go sort order) */
+struct LastTime { int64_t last; int unsorted = 0; __device__ __forceinline__ void operator()(uint32_t i, int64_t t) { if (i && t < last) unsorted = 1; last = t; } };
+
 __global__ void k_validate(DirP d, const int32_t *col_types, uint32_t *seg_rows, unsigned long long *totals /*[0]=rows [1]=page bytes*/,
                            uint32_t *max_rows, int *err) {
     uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,6 +81,13 @@ __global__ void k_validate(DirP d, const int32_t *col_types, uint32_t *seg_rows,
     size_t ti = (size_t)d.n_columns * d.n_segments + seg;
     TimeDesc t;
     int rc = parse_time_page(d.data + d.page_off[ti], d.page_len[ti], t);
+    if (rc == D_OK && t.rows == 0) rc = D_CORRUPT;
+    if (rc == D_OK) { /* the directory's time range must cover the page's times: bucket indices are derived from it and never re-checked */
+        LastTime lt; lt.last = t.t0;
+        if (t.kind == 0) lt.last = (int64_t)((uint64_t)t.t0 + (uint64_t)(t.rows - 1) * t.delta); /* const-delta: closed form */
+        else rc = decode_time_values(t, lt);
+        if (rc == D_OK && (t.t0 < d.seg_tmin[seg] || lt.last > d.seg_tmax[seg] || lt.last < t.t0 || lt.unsorted)) rc = D_CORRUPT;
+    }
     if (rc != D_OK) { report_err(err, rc, seg); seg_rows[seg] = 0; return; }
     seg_rows[seg] = t.rows;
     unsigned long long bytes = d.page_len[ti];
@@ -255,6 +265,7 @@ __global__ void k_window_reduce(DirP d, QueryP q, TileP tp, ChunkP ch) {
         if (cur_b == OG_NO_BUCKET || t >= we) {
             flush(false);
             cur_b = bucket_of(t, q.start, q.interval);
+            if (cur_b >= q.n_buckets) { report_err(ch.err, D_CORRUPT, seg); cur_b = OG_NO_BUCKET; break; } /* cannot happen on a validated shard */
             we = q.start + (int64_t)(cur_b + 1) * q.interval;
 #pragma unroll
             for (uint32_t c = 0; c < OG_MAX_CALLS; c++) parts[c] = part_empty();

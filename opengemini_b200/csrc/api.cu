@@ -256,8 +256,10 @@ static void window_of(int64_t interval, int64_t offset, int64_t tmin, int64_t tm
 } /* extern "C" */
 namespace { void free_plan(void *plan); }
 extern "C" {
+void og_query_free_merge_state(void *p);
 OG_API void og_query_destroy(og_query *q) {
     if (!q) return;
+    if (q->merge_state) og_query_free_merge_state(q->merge_state);
     free_plan(q->plan);
     for (void *p : q->scratch) cudaFree(p);
     for (int c = 0; c < OG_MAX_CALLS; c++) { cudaFree(q->dense[c].val); cudaFree(q->dense[c].ok); cudaFree(q->dense[c].tim); }
@@ -332,6 +334,10 @@ OG_API int og_query_create(og_shard *s, const og_query_desc *d_in, og_query **ou
      * so open-ended queries (opt.StartTime/EndTime = Min/MaxTime) get a bounded interval record. */
     int64_t gmin = std::max(d->tmin, s->tmin), gmax = std::min(d->tmax, s->tmax);
     if (gmin > gmax) gmin = gmax = d->tmin; /* no overlap: one empty window */
+    if (d->flags & OG_Q_QUERY_GRID) { /* one grid for every shard of a cross-shard query */
+        if (d_in->tmin <= MIN_TIME || d_in->tmax >= MAX_TIME) { set_error("OG_Q_QUERY_GRID needs a bounded time range"); delete q; return OG_E_INVAL; }
+        gmin = d->tmin; gmax = d->tmax;
+    }
     int64_t s0, e0, s1, e1;
     if (d->interval == 0) { s0 = gmin; e0 = gmax + 1; s1 = s0; e1 = e0; }
     else {
@@ -806,6 +812,11 @@ OG_API int og_query_merge_dense(og_query *q, const og_dense_view *other) {
     if (!q->ran) return OG_E_STATE;
     const QueryP &p = q->qp;
     if (other->n_groups != q->n_groups || other->n_buckets != p.n_buckets || other->n_cols != p.n_calls) { set_error("dense shapes differ"); return OG_E_INVAL; }
+    if (other->start != (q->desc.interval ? p.start : 0) || other->interval != (q->desc.interval ? p.interval : 0)) {
+        set_error("dense grids differ (start %lld vs %lld, interval %lld vs %lld): create the queries with OG_Q_QUERY_GRID", (long long)other->start,
+                  (long long)(q->desc.interval ? p.start : 0), (long long)other->interval, (long long)(q->desc.interval ? p.interval : 0));
+        return OG_E_INVAL;
+    }
     CU(cudaSetDevice(q->sh->device));
     GroupP mine, oth; memset(&mine, 0, sizeof mine); memset(&oth, 0, sizeof oth);
     mine.n_groups = oth.n_groups = q->n_groups;

@@ -104,12 +104,14 @@ __device__ __forceinline__ int parse_field_header(const uint8_t *p, uint32_t len
     if (typ != (uint8_t)col_type) return D_TYPE;
     if (len < 13) return D_CORRUPT;
     uint32_t nb = ld_be32(p + 1);
-    if (len - 1 < nb + 8) return D_CORRUPT;
+    if (13ull + (uint64_t)nb > (uint64_t)len) return D_CORRUPT; /* 64-bit: nb near 2^32 must not wrap the bound */
     h.bitmap = p + 5;
     h.bm_off = ld_be32(p + 5 + nb);
     h.nil_count = ld_be32(p + 9 + nb);
     h.block = p + 13 + nb; h.block_len = len - 13 - nb;
     h.rows = seg_rows;
+    /* the validity bits of the rows must lie inside the bitmap, and a page cannot hold more nulls than rows */
+    if (h.nil_count > seg_rows || ((uint64_t)h.bm_off + seg_rows + 7) / 8 > (uint64_t)nb) return D_CORRUPT;
     return D_OK;
 }
 __device__ __forceinline__ bool hdr_row_valid(const PageHdr &h, uint32_t i) {

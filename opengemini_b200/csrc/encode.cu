@@ -372,7 +372,7 @@ __global__ void k_synth_fill(og_synth_desc d, og_synth_column col, uint32_t colu
                              uint32_t segs_per_series, uint8_t *cells, uint8_t *okb) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_segments) return;
-    uint32_t seg = seg_begin + i, series = seg / segs_per_series, g = seg % segs_per_series;
+    uint32_t seg = seg_begin + i, series = d.series_base + seg / segs_per_series, g = seg % segs_per_series;
     uint32_t rps = d.rows_per_segment;
     uint64_t row0 = (uint64_t)g * rps;
     uint32_t n = (uint32_t)min((uint64_t)rps, (uint64_t)d.rows_per_series - row0);
@@ -469,7 +469,7 @@ OG_API int og_shard_synth(const og_synth_desc *dd, og_shard **out) {
     s->device = dev; s->n_series = d.n_series; s->n_segments = nseg; s->n_columns = d.n_columns;
     for (uint32_t c = 0; c < d.n_columns; c++) { s->col_types.push_back(d.columns[c].type); s->col_names.push_back("f" + std::to_string(c)); }
     s->sids.resize(d.n_series); s->h_series_seg_begin.resize((size_t)d.n_series + 1);
-    for (uint32_t i = 0; i < d.n_series; i++) { s->sids[i] = (uint64_t)i + 1; s->h_series_seg_begin[i] = i * sps; }
+    for (uint32_t i = 0; i < d.n_series; i++) { s->sids[i] = (uint64_t)d.series_base + i + 1; s->h_series_seg_begin[i] = i * sps; }
     s->h_series_seg_begin[d.n_series] = nseg;
     s->tmin = d.t0; s->tmax = d.t0 + (int64_t)(d.rows_per_series - 1) * d.dt;
     int rc;

@@ -73,6 +73,7 @@ struct FusedState {
         if (cur_b == OG_NO_BUCKET || t >= we) {
             flush(false);
             cur_b = bucket_of(t, q.start, q.interval);
+            if (cur_b >= q.n_buckets) { report_err(ch.err, D_CORRUPT, seg); cur_b = OG_NO_BUCKET; return; } /* cannot happen on a validated shard */
             we = q.start + (int64_t)(cur_b + 1) * q.interval;
 #pragma unroll
             for (int c = 0; c < NC; c++) parts[c] = part_empty();

@@ -79,6 +79,9 @@ enum { SEG_GENERAL = 0, SEG_FAST = 1, SEG_RAWX = 2 }; /* static per-segment clas
 #ifndef OG_IL_K
 #define OG_IL_K 8u              /* records per round */
 #endif
+#ifndef OG_IL_UNROLL
+#define OG_IL_UNROLL 8
+#endif
 #define OG_IL_NB (OG_IL_NW / OG_IL_B)
 #define OG_IL_ROWS (OG_IL_NW + 2u) /* + 2 mirror rows that repeat ring rows 0,1 so that three consecutive rows never wrap */
 #define OG_IL_PAD_WORDS 6u      /* words appended to every stream: the decoder may touch 77 + 64 + 32 bits past the last record */
@@ -104,6 +107,18 @@ struct IlP {
     const int64_t *lane_t0;      /* const-delta time page: t(r) = t0 + r*dt */
     const uint64_t *lane_dt;
 };
+
+/* floor(a / b) for a < 2^63 through a double-precision estimate and an exact 64-bit correction (a handful of instructions
+ * instead of the ~150 of the generic 64-bit division; the segment prologue needs six of them).  inv_b = 1.0 / (double)b. */
+__device__ __forceinline__ uint64_t udiv_est(uint64_t a, uint64_t b, double inv_b) {
+    const double qd = __ull2double_rn(a) * inv_b;
+    if ((a >> 63) || !(qd < 1125899906842624.0)) return a / b; /* quotient >= 2^50: the estimate could be off by more than a few units */
+    uint64_t q = (uint64_t)qd;
+    uint64_t r = a - q * b;
+    if ((int64_t)r < 0) { do { q--; r += b; } while ((int64_t)r < 0); }
+    else while (r >= b) { q++; r -= b; }
+    return q;
+}
 
 /* 64 bits of the stream at bit position p: ring rows (p>>5), +1, +2 of the lane's column */
 __device__ __forceinline__ uint64_t fetch64(uint32_t col, uint32_t p) {
@@ -148,6 +163,7 @@ __global__ void __maxnreg__(OG_FAST_MAXREG) k_fused_il(QueryP q, ChunkP ch, IlP 
     constexpr uint32_t NW = OG_IL_NW, B = OG_IL_B, NB = OG_IL_NB, K = OG_IL_K;
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr uint32_t WPB = OG_FAST_THREADS / 32;
+    constexpr int UNR = OG_IL_UNROLL;
     __shared__ __align__(128) uint32_t s_win[WPB * OG_IL_ROWS * 32];
     __shared__ __align__(8) uint64_t s_bar[WPB * NB];
     extern __shared__ __align__(8) uint8_t s_acc[]; /* FOLD: WPB x il_acc_bytes */
@@ -168,15 +184,17 @@ __global__ void __maxnreg__(OG_FAST_MAXREG) k_fused_il(QueryP q, ChunkP ch, IlP 
     const size_t e = 2 * (size_t)(seg - ch.seg_begin);
 
     uint32_t rows = 0, series = 0, r_lo = 0, r_hi = 0; bool rawx = false;
-    int64_t t0 = 0, dt = 1; uint64_t dtu = 1;
+    int64_t t0 = 0, dt = 1; uint64_t dtu = 1; double inv_dt = 1.0;
+    const double inv_iv = 1.0 / __ull2double_rn((uint64_t)q.interval);
     if (active) {
         const uint32_t rf = il.lane_rows[slot];
         rows = rf & ~OG_IL_RAWFLAG; rawx = (rf & OG_IL_RAWFLAG) != 0; series = il.lane_series[slot];
         t0 = il.lane_t0[slot]; dtu = il.lane_dt[slot]; dt = (int64_t)dtu;
+        inv_dt = 1.0 / __ull2double_rn(dtu);
         /* rows inside [tmin, tmax] (FilterByTime) */
         r_lo = 0; r_hi = rows - 1;
-        if (t0 < q.tmin) { uint64_t k = ((uint64_t)(q.tmin - t0) + dtu - 1) / dtu; r_lo = k > rows ? rows : (uint32_t)k; }
-        { int64_t t_last = t0 + (int64_t)(rows - 1) * dt; if (t_last > q.tmax) { if (q.tmax < t0) r_lo = rows; else r_hi = (uint32_t)((uint64_t)(q.tmax - t0) / dtu); } }
+        if (t0 < q.tmin) { uint64_t k = udiv_est((uint64_t)(q.tmin - t0) + dtu - 1, dtu, inv_dt); r_lo = k > rows ? rows : (uint32_t)k; }
+        { int64_t t_last = t0 + (int64_t)(rows - 1) * dt; if (t_last > q.tmax) { if (q.tmax < t0) r_lo = rows; else r_hi = (uint32_t)udiv_est((uint64_t)(q.tmax - t0), dtu, inv_dt); } }
         if (r_lo > r_hi || r_lo >= rows) { ch.edge_bucket[e] = OG_NO_BUCKET; ch.edge_bucket[e + 1] = OG_NO_BUCKET; active = false; }
     }
     if (!__any_sync(FULL, active)) return;
@@ -224,14 +242,14 @@ __global__ void __maxnreg__(OG_FAST_MAXREG) k_fused_il(QueryP q, ChunkP ch, IlP 
     uint32_t cur_b = 0, rb = 0xffffffffu, step_q = 0; uint64_t rem = 0, step_r = 0;
     if (active) {
         const int64_t t_lo = t0 + (int64_t)r_lo * dt;
-        cur_b = bucket_of(t_lo, q.start, q.interval);
+        cur_b = (uint32_t)udiv_est((uint64_t)(t_lo - q.start), (uint64_t)q.interval, inv_iv);
         const uint64_t ivl = (uint64_t)q.interval;
-        const uint64_t sq64 = ivl / dtu;
+        const uint64_t sq64 = udiv_est(ivl, dtu, inv_dt);
         step_q = sq64 > 0xffffffffull ? 0xffffffffu : (uint32_t)sq64;
         step_r = ivl - sq64 * dtu;
         /* rb = ceil((W - t0)/dt), W = start + (cur_b+1)*interval > t_lo >= t0 */
         uint64_t D = (uint64_t)(q.start + (int64_t)(cur_b + 1) * q.interval - t0) + dtu - 1;
-        uint64_t qq = D / dtu; rem = D - qq * dtu; rb = qq > 0xffffffffull ? 0xffffffffu : (uint32_t)qq;
+        uint64_t qq = udiv_est(D, dtu, inv_dt); rem = D - qq * dtu; rb = qq > 0xffffffffull ? 0xffffffffu : (uint32_t)qq;
     }
 
     /* ---- folding: the lanes share a time grid (same first row, cadence and row range), so a bucket means the same window to all of
@@ -248,7 +266,7 @@ __global__ void __maxnreg__(OG_FAST_MAXREG) k_fused_il(QueryP q, ChunkP ch, IlP 
         const uint32_t loL = __shfl_sync(FULL, r_lo, leader), hiL = __shfl_sync(FULL, r_hi, leader);
         b0 = __shfl_sync(FULL, cur_b, leader);
         const bool same = t0 == t0L && dtu == dtL && r_lo == loL && r_hi == hiL;
-        const uint32_t b_last = active ? bucket_of(t0 + (int64_t)r_hi * dt, q.start, q.interval) : b0;
+        const uint32_t b_last = active ? (uint32_t)udiv_est((uint64_t)(t0 + (int64_t)r_hi * dt - q.start), (uint64_t)q.interval, inv_iv) : b0;
         uni = __all_sync(FULL, !active || (same && b_last - b0 < OG_IL_WCAP));
         if (uni) {
             const uint32_t nacc = OG_IL_WCAP * q.n_calls;
@@ -425,7 +443,7 @@ __global__ void __maxnreg__(OG_FAST_MAXREG) k_fused_il(QueryP q, ChunkP ch, IlP 
         bool go = done || need <= ready_b * B; /* a lane that could touch rows not resident yet sits the round out */
         uint32_t run = __reduce_min_sync(FULL, go ? n_ev : 0u); /* finished lanes have n_ev near 2^32 */
         if (run >= K) { /* every lane runs, no boundary ahead */
-#pragma unroll
+#pragma unroll UNR
             for (uint32_t k = 0; k < K; k++) record(k);
             n_ev -= K;
 #ifdef OG_IL_STATS

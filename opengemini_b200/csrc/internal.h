@@ -19,6 +19,7 @@ namespace ogpu {
 
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+int ensure_device(); /* bind the calling thread to the library's device (og_init(0) on first use) */
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ::ogpu::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
 
 struct DevBuf { /* RAII-less helper: explicit free */
@@ -120,4 +121,5 @@ struct og_query {
     int *d_err = nullptr;
     void *plan = nullptr; /* ogpu::Plan (agg_kernels.cuh types) */
     std::vector<cudaEvent_t> main_ev; /* event pairs around the dominant decode+reduce kernels */
+    void *merge_state = nullptr;      /* og_merge_state of the last og_query_allreduce (comm.cu) */
 };

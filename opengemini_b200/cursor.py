@@ -93,12 +93,12 @@ class Shard:
 
     @classmethod
     def synth(cls, n_series, rows_per_series, columns, t0=1_700_000_000_000_000_000, dt=1_000_000_000, seed=1,
-              rows_per_segment=1000):
+              rows_per_segment=1000, series_base=0):
         """columns: list of (type, dist, null_permille). Builds the shard on the device with the encode kernels."""
         cols = (L.SynthColumn * len(columns))()
         for i, (t, dist, npm) in enumerate(columns):
             cols[i].type, cols[i].dist, cols[i].null_permille = t, dist, npm
-        d = L.SynthDesc(n_series, rows_per_series, rows_per_segment, t0, dt, seed, len(columns), cols)
+        d = L.SynthDesc(n_series, rows_per_series, rows_per_segment, t0, dt, seed, len(columns), cols, series_base)
         h = C.c_void_p()
         L.check(L.lib().og_shard_synth(C.byref(d), C.byref(h)), "og_shard_synth")
         return cls(h.value)
@@ -255,3 +255,44 @@ class AggQuery:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """The library's own NCCL communicator (og_comm_*): rank 0 creates the 128-byte id, the host passes it to the other
+    ranks through whatever channel it has (a Go host: its RPC layer; bench.py: torch.distributed's store), every rank
+    then joins.  allreduce(q) merges q's dense interval record over all ranks in place (og_query_allreduce)."""
+
+    def __init__(self, handle, rank, world):
+        self.h, self.rank, self.world = handle, rank, world
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        L.check(L.lib().og_comm_unique_id(buf), "og_comm_unique_id")
+        return bytes(buf)
+
+    @classmethod
+    def init_rank(cls, uid, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        h = C.c_void_p()
+        L.check(L.lib().og_comm_init_rank(buf, int(rank), int(world), C.byref(h)), "og_comm_init_rank")
+        return cls(h, rank, world)
+
+    def info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        L.check(L.lib().og_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)), "og_comm_info")
+        return dict(rank=r.value, world=w.value, nccl_version=v.value)
+
+    def allreduce_f64(self, vals, op="sum"):
+        arr = (C.c_double * len(vals))(*vals)
+        L.check(L.lib().og_comm_allreduce_f64(self.h, arr, len(vals), 1 if op == "max" else 0), "og_comm_allreduce_f64")
+        return list(arr)
+
+    def allreduce(self, query):
+        L.check(L.lib().og_query_allreduce(query.h, self.h), "og_query_allreduce")
+
+    def close(self):
+        if self.h:
+            L.lib().og_comm_destroy(self.h)
+            self.h = None
+

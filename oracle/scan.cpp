@@ -326,7 +326,7 @@ int build_synth_shard(const og_synth_desc &d, HostShard &out, int threads) {
     Bytes &data = bufs[(size_t)tid];
     std::vector<int64_t> times(rps);
     for (uint32_t s = s_a; s < s_b; s++) {
-        out.sids[s] = (uint64_t)s + 1;
+        out.sids[s] = (uint64_t)d.series_base + s + 1;
         out.series_seg_begin[s] = s * segs_per_series;
         for (uint32_t c = 0; c <= d.n_columns; c++) {
             data.insert(data.end(), 4, 0); /* crc32 placeholder (not verified by the attached read path) */
@@ -344,19 +344,20 @@ int build_synth_shard(const og_synth_desc &d, HostShard &out, int threads) {
                     const og_synth_column &sc = d.columns[c];
                     ColVal cv;
                     int64_t walk = 0;
+                    const uint32_t ps = d.series_base + s; /* position of the series in the synthetic population */
                     for (uint32_t i = 0; i < n; i++) {
                         uint64_t row = row0 + i;
-                        bool nil = og_synth_is_null(d.seed, c, s, row, sc.null_permille);
+                        bool nil = og_synth_is_null(d.seed, c, ps, row, sc.null_permille);
                         switch (sc.dist) {
-                        case OG_SYNTH_F_HI: if (nil) cv.append_null(OG_TYPE_FLOAT, false); else cv.append_float(og_synth_f_hi(d.seed, c, s, row)); break;
+                        case OG_SYNTH_F_HI: if (nil) cv.append_null(OG_TYPE_FLOAT, false); else cv.append_float(og_synth_f_hi(d.seed, c, ps, row)); break;
                         case OG_SYNTH_F_LO:
-                            walk = i == 0 ? og_synth_walk_first(d.seed, c, s, g, 1) : walk + og_synth_f_lo_step(d.seed, c, s, row);
+                            walk = i == 0 ? og_synth_walk_first(d.seed, c, ps, g, 1) : walk + og_synth_f_lo_step(d.seed, c, ps, row);
                             if (nil) cv.append_null(OG_TYPE_FLOAT, false); else cv.append_float((double)walk); break;
                         case OG_SYNTH_INT_WALK:
-                            walk = i == 0 ? og_synth_walk_first(d.seed, c, s, g, 0) : walk + og_synth_int_step(d.seed, c, s, row);
+                            walk = i == 0 ? og_synth_walk_first(d.seed, c, ps, g, 0) : walk + og_synth_int_step(d.seed, c, ps, row);
                             if (nil) cv.append_null(OG_TYPE_INT, false); else cv.append_integer(walk); break;
                         default:
-                            if (nil) cv.append_null(OG_TYPE_BOOL, false); else cv.append_boolean(og_synth_bool(d.seed, c, s, row) != 0); break;
+                            if (nil) cv.append_null(OG_TYPE_BOOL, false); else cv.append_boolean(og_synth_bool(d.seed, c, ps, row) != 0); break;
                         }
                     }
                     rc = encode_field_page(cv, sc.type, data);

@@ -153,12 +153,12 @@ class HostShard:
     """Synthetic shard built on the host with the oracle's restated encoders."""
 
     def __init__(self, n_series, rows_per_series, columns, t0=1_700_000_000_000_000_000, dt=1_000_000_000, seed=1, rows_per_segment=1000,
-                 threads=1):
+                 threads=1, series_base=0):
         cols = (L.SynthColumn * len(columns))()
         for i, (t, dist, npm) in enumerate(columns):
             cols[i].type, cols[i].dist, cols[i].null_permille = t, dist, npm
         self._cols = cols
-        d = L.SynthDesc(n_series, rows_per_series, rows_per_segment, t0, dt, seed, len(columns), cols)
+        d = L.SynthDesc(n_series, rows_per_series, rows_per_segment, t0, dt, seed, len(columns), cols, series_base)
         st = C.c_int()
         lib().ogo_synth_build_mt.restype = C.c_void_p
         lib().ogo_synth_build_mt.argtypes = [C.POINTER(L.SynthDesc), C.c_int, C.POINTER(C.c_int)]
