@@ -405,17 +405,30 @@ __global__ void __maxnreg__(OG_FAST_MAXREG) k_fused_il(QueryP q, ChunkP ch, IlP 
         val ^= sig << tr;
         qp = p - sr;
     };
-    auto record = [&](uint32_t k_in_run) {
-        /* accumulate the current row; n_ev counts down once per run of records, k_in_run is the offset inside it */
+    auto accumulate = [&](uint32_t k_in_run) { /* the current row; n_ev counts down once per run of records, k_in_run is the offset inside it */
         if (FM & FM_SUM) sum = sum + u2d(val);
         if (FM & FM_MIN) { if (mn > u2d(val)) { mn = u2d(val); if (TIMES) n_mn = n_ev - k_in_run; } }
         if (FM & FM_MAX) { if (mx < u2d(val)) { mx = u2d(val); if (TIMES) n_mx = n_ev - k_in_run; } }
         if (FM & FM_LAST) lastv = val;
-        /* next record */
-        const uint64_t x = fetch64(col, qp);
+    };
+    auto record = [&](uint32_t k_in_run) {
+        accumulate(k_in_run);
+        const uint64_t x = fetch64(col, qp); /* next record */
         const bool slow = (((uint32_t)(x >> 32) & CM) ^ CE) != 0;
-        if (__builtin_expect(slow, 0)) slow_record(); /* kept out of the straight-line path */
+        if (slow) slow_record();
         else { val ^= x & MASK; qp += kfast; } /* '10' with the window in place, raw delta, or an idle lane */
+    };
+    /* two records with both fetches issued up front: record k+1 starts kfast bits after record k when k is an in-place '10'
+     * (it nearly always is), so its 64 bits can be loaded before k has been tested — the two shared-memory round trips overlap
+     * instead of forming one dependent chain per record.  A wrong guess costs a re-fetch on the general path. */
+    auto record2 = [&](uint32_t k_in_run) {
+        const uint64_t x0 = fetch64(col, qp), x1 = fetch64(col, qp + kfast);
+        accumulate(k_in_run);
+        if ((((uint32_t)(x0 >> 32) & CM) ^ CE) != 0) { slow_record(); record(k_in_run + 1); return; }
+        val ^= x0 & MASK; qp += kfast;
+        accumulate(k_in_run + 1);
+        if ((((uint32_t)(x1 >> 32) & CM) ^ CE) != 0) slow_record();
+        else { val ^= x1 & MASK; qp += kfast; }
     };
 
     /* Rounds.  Every round the slowest live lane decodes K records, so 32 lanes finish within 32 * (rows / K + 1) eventful rounds.
@@ -443,8 +456,9 @@ __global__ void __maxnreg__(OG_FAST_MAXREG) k_fused_il(QueryP q, ChunkP ch, IlP 
         bool go = done || need <= ready_b * B; /* a lane that could touch rows not resident yet sits the round out */
         uint32_t run = __reduce_min_sync(FULL, go ? n_ev : 0u); /* finished lanes have n_ev near 2^32 */
         if (run >= K) { /* every lane runs, no boundary ahead */
+            static_assert(K % 2 == 0, "records are decoded in pairs");
 #pragma unroll UNR
-            for (uint32_t k = 0; k < K; k++) record(k);
+            for (uint32_t k = 0; k < K; k += 2) record2(k);
             n_ev -= K;
 #ifdef OG_IL_STATS
             st_common++;
