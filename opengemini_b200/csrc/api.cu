@@ -11,6 +11,8 @@
 #include "agg_kernels.cuh"
 #include "fused.cuh"
 #include "il_build.cuh"
+#include "snappy_load.cuh"
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include "internal.h"
 
@@ -52,7 +54,7 @@ static DirP make_dir(const og_shard *s) {
 }
 
 /* derive seg_series / seg_rows / totals and validate codecs; shared by og_shard_open and og_shard_synth */
-int shard_finalize(og_shard *s) {
+int shard_finalize(og_shard *s, bool scan_snappy) {
     int rc;
     s->il.resize(s->n_columns); /* sized once here: queries only read/lock individual entries later */
     if ((rc = dalloc(&s->d_seg_series, s->n_segments))) return rc;
@@ -65,6 +67,37 @@ int shard_finalize(og_shard *s) {
     CU(cudaMemcpy(d_types, s->col_types.data(), s->n_columns * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemset(d_tot, 0, 16)); CU(cudaMemset(d_max, 0, 4)); CU(cudaMemset(d_err, 0, 8));
     if (s->n_series) k_fill_seg_series<<<s->n_series, 128>>>(s->d_series_seg_begin, s->n_series, s->d_seg_series);
+    if (s->n_segments && scan_snappy) { /* Snappy pages -> raw pages appended behind the data (snappy_load.cuh) */
+        const size_t n_pages = (size_t)(s->n_columns + 1) * s->n_segments;
+        uint32_t *tr_size; unsigned long long *d_cnt;
+        if ((rc = dalloc(&tr_size, n_pages))) return rc;
+        if ((rc = dalloc(&d_cnt, 3))) { cudaFree(tr_size); return rc; }
+        struct Free2 { void *a, *b; ~Free2() { cudaFree(a); cudaFree(b); } } f2{tr_size, d_cnt};
+        CU(cudaMemset(d_cnt, 0, 24));
+        k_snappy_scan<<<(s->n_segments + 127) / 128, 128>>>(make_dir(s), d_types, tr_size, d_cnt);
+        unsigned long long cnt[3];
+        CU(cudaMemcpy(cnt, d_cnt, 24, cudaMemcpyDeviceToHost));
+        if (cnt[0]) {
+            if (!s->owns_data) { set_error("shard has %llu Snappy pages: they are transcoded at open, which needs a library-owned copy of the data (do not pass OG_SHARD_DEVICE_DATA)", cnt[0]); return OG_E_UNSUPPORTED; }
+            uint64_t *tr_off; void *tmp = nullptr; size_t tb = 0;
+            if ((rc = dalloc(&tr_off, n_pages))) return rc;
+            struct Free1 { void *a; ~Free1() { cudaFree(a); } } f1{tr_off};
+            CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, tr_size, tr_off, (int)n_pages));
+            CU(cudaMalloc(&tmp, tb ? tb : 1));
+            struct Free3 { void *a; ~Free3() { cudaFree(a); } } f3{tmp};
+            CU(cub::DeviceScan::ExclusiveSum(tmp, tb, tr_size, tr_off, (int)n_pages));
+            const uint64_t new_base = (s->data_len + 15) & ~15ull, new_len = new_base + cnt[2];
+            uint8_t *nd;
+            if ((rc = dalloc(&nd, (size_t)new_len + 1024))) return rc;
+            CU(cudaMemcpy(nd, s->d_data, s->data_len, cudaMemcpyDeviceToDevice));
+            CU(cudaMemset(nd + s->data_len, 0, new_len + 1024 - s->data_len));
+            k_snappy_transcode<<<(unsigned)((n_pages + 127) / 128), 128>>>(make_dir(s), tr_size, tr_off, nd, new_base, s->d_page_off, s->d_page_len, d_err);
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+            cudaFree(s->d_data); s->d_data = nd; s->data_len = new_len;
+            s->snappy_pages = cnt[0]; s->snappy_bytes_in = cnt[1]; s->snappy_bytes_out = cnt[2];
+        }
+    }
     if (s->n_segments) k_validate<<<(s->n_segments + 127) / 128, 128>>>(make_dir(s), d_types, s->d_seg_rows, d_tot, d_max, d_err);
     CU(cudaGetLastError());
     unsigned long long tot[2]; int err[2]; uint32_t mx;
@@ -76,7 +109,8 @@ int shard_finalize(og_shard *s) {
         set_error("segment %d: %s page (device validation code %d)", err[1], err[0] == D_UNSUPPORTED ? "unsupported codec in" : err[0] == D_TYPE ? "type mismatch in" : "corrupt", err[0]);
         return map_dev_err(err[0]);
     }
-    s->n_rows = tot[0]; s->page_bytes = tot[1]; s->max_seg_rows = mx;
+    s->n_rows = tot[0]; s->page_bytes = tot[1] - s->snappy_bytes_out + s->snappy_bytes_in; /* algorithmic bytes = the pages as stored */
+    s->max_seg_rows = mx;
     return OG_OK;
 }
 
@@ -198,7 +232,7 @@ OG_API int og_shard_open(const og_shard_desc *d, og_shard **out) {
     TRYCU(cudaMemcpy(s->d_page_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
     TRYCU(cudaMemcpy(s->d_page_len, len.data(), len.size() * 4, cudaMemcpyHostToDevice));
     TRYCU(cudaMemcpy(s->d_sids, d->sids, (size_t)d->n_series * 8, cudaMemcpyHostToDevice));
-    TRY(shard_finalize(s));
+    TRY(shard_finalize(s, true));
     *out = s;
     return OG_OK;
 }

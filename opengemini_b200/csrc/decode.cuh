@@ -18,7 +18,7 @@
 
 namespace ogpu {
 
-enum { D_OK = 0, D_UNSUPPORTED = 1, D_CORRUPT = 2, D_TYPE = 3, D_WATCHDOG = 4 /* a device-side progress guard fired (reported as OG_E_CUDA) */ };
+enum { D_OK = 0, D_UNSUPPORTED = 1, D_CORRUPT = 2, D_TYPE = 3, D_WATCHDOG = 4, D_SNAPPY = 5 /* internal: Snappy page, transcoded to a raw page when the shard is opened */ /* a device-side progress guard fired (reported as OG_E_CUDA) */ };
 
 /* ---------------- unaligned big-endian loads on top of aligned 64-bit __ldg ---------------- */
 __device__ __forceinline__ uint64_t bswap64(uint64_t v) {
@@ -53,6 +53,63 @@ __device__ __forceinline__ int ld_uvarint(const uint8_t *p, uint32_t len, uint64
     return 0;
 }
 __device__ __forceinline__ int64_t zigzag_dec(uint64_t u) { return (int64_t)(u >> 1) ^ -(int64_t)(u & 1); }
+
+/* ---------------- Snappy block format (golang/snappy, klauspost/compress snappy: lib/compress/compress.go:132-144) ----------------
+ * [uvarint decoded length] then elements: tag&3 == 0 literal (len-1 in the upper six bits, 60..63 = 1..4 length bytes follow),
+ * 1 copy with 11-bit offset (len 4..11), 2 copy with 16-bit offset, 3 copy with 32-bit offset (len 1..64).
+ * One thread decodes one block into `out` (load-time transcode of Snappy pages, api.cu); returns D_OK / D_CORRUPT. */
+__device__ __forceinline__ int snappy_decoded_len(const uint8_t *in, uint32_t len, uint32_t *n, uint32_t *hdr) {
+    uint64_t v; int k = ld_uvarint(in, len, &v);
+    if (k <= 0 || v > 0xffffffffull) return D_CORRUPT;
+    *n = (uint32_t)v; *hdr = (uint32_t)k;
+    return D_OK;
+}
+__device__ inline int snappy_decode_dev(const uint8_t *in, uint32_t len, uint8_t *out, uint32_t out_cap, uint32_t *out_len) {
+    uint32_t dlen, s;
+    if (snappy_decoded_len(in, len, &dlen, &s) != D_OK || dlen > out_cap) return D_CORRUPT;
+    uint32_t d = 0;
+    while (s < len) {
+        const uint32_t tag = __ldg(in + s);
+        uint32_t length, offset;
+        switch (tag & 3) {
+        case 0: {
+            uint32_t x = tag >> 2;
+            if (x < 60) s += 1;
+            else {
+                const uint32_t nb = x - 59;
+                if (s + 1 + nb > len) return D_CORRUPT;
+                x = 0;
+                for (uint32_t i = 0; i < nb; i++) x |= (uint32_t)__ldg(in + s + 1 + i) << (8 * i);
+                s += 1 + nb;
+            }
+            length = x + 1;
+            if (length == 0 || length > len - s || length > dlen - d) return D_CORRUPT;
+            for (uint32_t i = 0; i < length; i++) out[d + i] = __ldg(in + s + i);
+            d += length; s += length;
+            continue;
+        }
+        case 1:
+            if (s + 2 > len) return D_CORRUPT;
+            length = 4 + ((tag >> 2) & 7); offset = ((tag & 0xe0) << 3) | __ldg(in + s + 1); s += 2;
+            break;
+        case 2:
+            if (s + 3 > len) return D_CORRUPT;
+            length = 1 + (tag >> 2); offset = __ldg(in + s + 1) | ((uint32_t)__ldg(in + s + 2) << 8); s += 3;
+            break;
+        default:
+            if (s + 5 > len) return D_CORRUPT;
+            length = 1 + (tag >> 2);
+            offset = __ldg(in + s + 1) | ((uint32_t)__ldg(in + s + 2) << 8) | ((uint32_t)__ldg(in + s + 3) << 16) | ((uint32_t)__ldg(in + s + 4) << 24); s += 5;
+            break;
+        }
+        if (offset == 0 || offset > d || length > dlen - d) return D_CORRUPT;
+        for (uint32_t i = 0; i < length; i++) out[d + i] = out[d + i - offset]; /* byte by byte: overlapping copies repeat a pattern */
+        d += length;
+    }
+    if (d != dlen) return D_CORRUPT;
+    *out_len = d;
+    return D_OK;
+}
 
 /* ---------------- MSB-first bit reader over an unaligned byte stream ---------------- */
 struct BitReader {
@@ -168,7 +225,7 @@ __device__ __forceinline__ int parse_time_page(const uint8_t *p, uint32_t len, T
         t.t0 = t.n_words ? zigzag_dec(ld_be64(t.words)) : 0; t.delta = 0;
         return D_OK;
     }
-    return tag == 3 ? D_UNSUPPORTED : D_CORRUPT; /* snappy */
+    return tag == 3 ? D_SNAPPY : D_CORRUPT; /* snappyDecoding :274: transcoded at shard open */
 }
 
 /* simple8b selector table (simple8b/encoding.go:193-210) */

@@ -24,7 +24,7 @@
 
 namespace ogpu {
 
-int shard_finalize(og_shard *s); /* api.cu */
+int shard_finalize(og_shard *s, bool scan_snappy); /* api.cu */
 int ensure_device();              /* api.cu */
 
 #define PAGE_STRIDE 8704u /* staging bytes per page: worst case 13 + 125 + 1 + 8000 (raw) rounded up, 8-byte aligned */
@@ -537,7 +537,7 @@ OG_API int og_shard_synth(const og_synth_desc *dd, og_shard **out) {
     if (fl & 16) { set_error("synthetic blob overflow"); og_shard_close(s); return OG_E_NOMEM; }
     STRYCU(cudaMemset(s->d_data + base, 0, std::min<uint64_t>(1024, est + 1024 - base)));
     s->data_len = base;
-    STRY(shard_finalize(s));
+    STRY(shard_finalize(s, false));
     *out = s;
     return OG_OK;
 }

@@ -34,6 +34,7 @@ struct og_shard {
     uint32_t n_series = 0, n_segments = 0, n_columns = 0;
     uint32_t max_seg_rows = 0;
     uint64_t n_rows = 0, page_bytes = 0;
+    uint64_t snappy_pages = 0, snappy_bytes_in = 0, snappy_bytes_out = 0; /* Snappy pages transcoded to raw at open */
     int64_t tmin = 0, tmax = 0;
     std::vector<uint64_t> sids;
     std::vector<int32_t> col_types;

@@ -107,6 +107,11 @@ OGO_API void *ogo_scan(const og_shard_desc *sh, const og_query_desc *q, int thre
     if (rc != E_OK) { delete r; return nullptr; }
     return r;
 }
+OGO_API void *ogo_fast_scan(const og_shard_desc *sh, const og_query_desc *q, int threads, uint32_t s0, uint32_t s1, int *status) {
+    ScanResult *r = new ScanResult; int rc = fast_scan_aggregate(*sh, *q, threads, s0, s1, *r); if (status) *status = rc;
+    if (rc != E_OK) { delete r; return nullptr; }
+    return r;
+}
 OGO_API void ogo_scan_dims(void *h, uint32_t *n_groups, uint32_t *n_buckets, int64_t *start, int64_t *interval,
                            uint64_t *rows, uint64_t *segs, uint64_t *bytes) {
     ScanResult *r = (ScanResult *)h;

@@ -185,6 +185,12 @@ struct ScanResult {
 int scan_aggregate(const og_shard_desc &shard, const og_query_desc &q, int threads, uint32_t series_begin,
                    uint32_t series_end, ScanResult &out);
 
+/* The CPU BASELINE leg for the headline query shape (fast_scan.cpp): the same path with the reference's batch Gorilla decoder
+ * (64-bit cached bit reader, batch_float.go:308-347) instead of the checker's bit-serial one.  E_UNSUPPORTED for anything but one
+ * float column, no WHERE, one tagset, count/sum(/min/max in multi-call queries) over Gorilla/raw pages with const-delta times. */
+int fast_scan_aggregate(const og_shard_desc &shard, const og_query_desc &q, int threads, uint32_t series_begin,
+                        uint32_t series_end, ScanResult &out);
+
 /* synthetic shard builder (host): same distributions as include/ogpu_synth.h, encoded with the restated encoders */
 struct HostShard {
     Bytes data;

@@ -389,6 +389,7 @@ int build_synth_shard(const og_synth_desc &d, HostShard &out, int threads) {
         Bytes().swap(bufs[(size_t)t]);
     }
     out.series_seg_begin[d.n_series] = nseg;
+    out.data.reserve(out.data.size() + 32); /* word-granular readers (fast_scan.cpp) may look a few bytes past the last page; desc().data_len excludes the slack */
     return E_OK;
 }
 

@@ -38,6 +38,8 @@ def lib():
         _lib.ogo_shard_desc.argtypes = [C.c_void_p, C.POINTER(L.ShardDesc)]
         _lib.ogo_shard_free.argtypes = [C.c_void_p]
         _lib.ogo_scan.restype = C.c_void_p
+        _lib.ogo_fast_scan.restype = C.c_void_p
+        _lib.ogo_fast_scan.argtypes = [C.POINTER(L.ShardDesc), C.POINTER(L.QueryDesc), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
         _lib.ogo_scan.argtypes = [C.POINTER(L.ShardDesc), C.POINTER(L.QueryDesc), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
         _lib.ogo_scan_dims.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         _lib.ogo_scan_col.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -218,12 +220,15 @@ def shard_desc_from_export(ex):
     return d
 
 
-def scan(shard_desc, query_desc, threads=1, s0=0, s1=0xFFFFFFFF):
-    """Run the reference-structured CPU pipeline. Returns dict like AggQuery.dense_host()."""
+def scan(shard_desc, query_desc, threads=1, s0=0, s1=0xFFFFFFFF, fast=False):
+    """Run the reference-structured CPU pipeline. Returns dict like AggQuery.dense_host().
+    fast=True: the CPU-baseline leg (oracle/fast_scan.cpp: batch Gorilla decode with a 64-bit cached bit reader) for the
+    headline query shape; use it on HostShard descriptors (it may read a few bytes past the last page)."""
     st = C.c_int()
-    h = lib().ogo_scan(C.byref(shard_desc), C.byref(query_desc), threads, s0, s1, C.byref(st))
+    fn = lib().ogo_fast_scan if fast else lib().ogo_scan
+    h = fn(C.byref(shard_desc), C.byref(query_desc), threads, s0, s1, C.byref(st))
     if not h:
-        raise ValueError(f"ogo_scan rc={st.value}")
+        raise ValueError(f"{'ogo_fast_scan' if fast else 'ogo_scan'} rc={st.value}")
     try:
         ng, nb = C.c_uint32(), C.c_uint32()
         start, iv = C.c_int64(), C.c_int64()

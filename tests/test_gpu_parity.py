@@ -226,7 +226,7 @@ def test_unsupported_and_corrupt_pages_fail_cleanly():
     t = T0 + np.arange(n, dtype=np.int64) * SEC
     tp = oracle.time_page_encode(t)
     good = oracle.field_page_encode(L.TYPE_FLOAT, 100 + np.random.default_rng(1).random(n))
-    for tag, want in ((0x20, L.OG_E_UNSUPPORTED), (0x60, L.OG_E_UNSUPPORTED), (0x70, L.OG_E_CORRUPT)):
+    for tag, want in ((0x20, L.OG_E_CORRUPT), (0x60, L.OG_E_UNSUPPORTED), (0x70, L.OG_E_CORRUPT)):  # 0x20: Snappy tag over Gorilla bytes = a corrupt Snappy block
         bad = good.copy(); bad[5] = tag  # block tag byte after the 5-byte Full header
         with pytest.raises(L.OgpuError) as ei:
             _one_segment_shard(L.TYPE_FLOAT, bad, tp, t)
