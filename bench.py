@@ -408,6 +408,21 @@ def run_ours(a):
     total_rows = rows_t.item()
     value = total_rows * a.steps / (dev_ms_max / 1e3)
 
+    # warm end-to-end: the shard stays resident in HBM (the deployment this library is built for: a shard is uploaded once and
+    # queried many times); a step = og_query_run + draining og_query_next into host records
+    resident = None
+    if not a.no_e2e:
+        r_steps = max(1, min(a.steps, 5))
+        torch.cuda.synchronize()
+        tr0 = time.perf_counter()
+        for _ in range(r_steps):
+            q.run()
+            if comm is not None:
+                comm.allreduce(q)
+            out_rows_r = sum(rec["rows"] for rec in q.records())
+        tr = time.perf_counter() - tr0
+        resident = {"value": float(info["n_rows"]) * world * r_steps / tr, "unit": "rows/s", "ms_per_step": tr / r_steps * 1e3, "steps": r_steps, "out_rows": out_rows_r,
+                    "what": "og_query_run + og_query_next until OG_EOF on the HBM-resident shard (host wall clock, D2H of the result inside)"}
     verify = verify_answer(a, L, sh, q, calls, tmax, rank, info) if not a.no_verify else None
     if comm is not None and not a.no_verify:
         vm = verify_merge(a, L, comm, rank, world)
@@ -492,6 +507,8 @@ def run_ours(a):
         d2h_full = int(st["out_bytes"])
         e2e = {"value": e_rows * e_steps / et.item(), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": max(d2h, d2h_full),
                "sample": f"{ns} series x {a.rows} rows per GPU per step (host-resident, pinned), og_shard_open + og_query_run + og_query_next",
+               "resident": resident,
+               "sample_note": "2000 of the 10000 series per step: pinning and re-uploading the full 61 GB shard every step would take minutes; rates, not totals, are compared",
                "steps": e_steps, "phase_ms_per_step": {k: round(v / e_steps, 2) for k, v in phases.items()}, "ms_per_step": et.item() / e_steps * 1e3, "out_rows": out_rows}
         del pinned
 

@@ -224,6 +224,9 @@ OG_API int og_device_count(void);
 OG_API const char *og_strerror(int status);
 OG_API const char *og_last_error(void);            /* thread-local detail message of the last failing call */
 OG_API const char *og_version(void);
+/* Device buffers of closed shards and destroyed queries stay in the device's memory pool for reuse (open/close loops do not pay
+ * cudaMalloc/cudaFree); this hands the unused part back to the driver. */
+OG_API int og_release_cached_memory(void);
 
 /* ---- shard ---- */
 OG_API int og_shard_open(const og_shard_desc *desc, og_shard **out);

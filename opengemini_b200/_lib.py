@@ -100,7 +100,7 @@ EXPORTS = [
     "og_shard_info", "og_query_create", "og_query_run", "og_query_next", "og_query_dense", "og_query_stats",
     "og_query_abort", "og_query_destroy", "og_query_merge_dense", "og_decode_segment", "og_decode_column_device",
     "og_shard_synth", "og_shard_layout_get", "og_shard_export", "og_encode_pages",
-    "og_comm_unique_id", "og_comm_init_rank", "og_comm_destroy", "og_comm_info", "og_comm_allreduce_f64", "og_query_allreduce",
+    "og_release_cached_memory", "og_comm_unique_id", "og_comm_init_rank", "og_comm_destroy", "og_comm_info", "og_comm_allreduce_f64", "og_query_allreduce",
 ]
 
 _lib = None

@@ -27,6 +27,16 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return OG_E_CUDA;
 }
 static int g_device = -1;
+cudaError_t dev_mem_info(size_t *free_b, size_t *total_b) {
+    cudaError_t e = cudaMemGetInfo(free_b, total_b);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool; uint64_t reserved = 0, used = 0; int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used) *free_b += (size_t)(reserved - used);
+    else cudaGetLastError();
+    return cudaSuccess;
+}
 
 static int map_dev_err(int code) {
     switch (code) {
@@ -40,7 +50,7 @@ static int map_dev_err(int code) {
 template <class T> static int dalloc(T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    cudaError_t e = dev_malloc((void **)p, n * sizeof(T));
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? OG_E_NOMEM : OG_E_CUDA; }
     return OG_OK;
 }
@@ -71,8 +81,8 @@ int shard_finalize(og_shard *s, bool scan_snappy) {
         const size_t n_pages = (size_t)(s->n_columns + 1) * s->n_segments;
         uint32_t *tr_size; unsigned long long *d_cnt;
         if ((rc = dalloc(&tr_size, n_pages))) return rc;
-        if ((rc = dalloc(&d_cnt, 3))) { cudaFree(tr_size); return rc; }
-        struct Free2 { void *a, *b; ~Free2() { cudaFree(a); cudaFree(b); } } f2{tr_size, d_cnt};
+        if ((rc = dalloc(&d_cnt, 3))) { dev_free(tr_size); return rc; }
+        struct Free2 { void *a, *b; ~Free2() { dev_free(a); dev_free(b); } } f2{tr_size, d_cnt};
         CU(cudaMemset(d_cnt, 0, 24));
         k_snappy_scan<<<(s->n_segments + 127) / 128, 128>>>(make_dir(s), d_types, tr_size, d_cnt);
         unsigned long long cnt[3];
@@ -81,10 +91,10 @@ int shard_finalize(og_shard *s, bool scan_snappy) {
             if (!s->owns_data) { set_error("shard has %llu Snappy pages: they are transcoded at open, which needs a library-owned copy of the data (do not pass OG_SHARD_DEVICE_DATA)", cnt[0]); return OG_E_UNSUPPORTED; }
             uint64_t *tr_off; void *tmp = nullptr; size_t tb = 0;
             if ((rc = dalloc(&tr_off, n_pages))) return rc;
-            struct Free1 { void *a; ~Free1() { cudaFree(a); } } f1{tr_off};
+            struct Free1 { void *a; ~Free1() { dev_free(a); } } f1{tr_off};
             CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, tr_size, tr_off, (int)n_pages));
-            CU(cudaMalloc(&tmp, tb ? tb : 1));
-            struct Free3 { void *a; ~Free3() { cudaFree(a); } } f3{tmp};
+            CU(dev_malloc((void **)&tmp, tb ? tb : 1));
+            struct Free3 { void *a; ~Free3() { dev_free(a); } } f3{tmp};
             CU(cub::DeviceScan::ExclusiveSum(tmp, tb, tr_size, tr_off, (int)n_pages));
             const uint64_t new_base = (s->data_len + 15) & ~15ull, new_len = new_base + cnt[2];
             uint8_t *nd;
@@ -94,7 +104,7 @@ int shard_finalize(og_shard *s, bool scan_snappy) {
             k_snappy_transcode<<<(unsigned)((n_pages + 127) / 128), 128>>>(make_dir(s), tr_size, tr_off, nd, new_base, s->d_page_off, s->d_page_len, d_err);
             CU(cudaGetLastError());
             CU(cudaDeviceSynchronize());
-            cudaFree(s->d_data); s->d_data = nd; s->data_len = new_len;
+            dev_free(s->d_data); s->d_data = nd; s->data_len = new_len;
             s->snappy_pages = cnt[0]; s->snappy_bytes_in = cnt[1]; s->snappy_bytes_out = cnt[2];
         }
     }
@@ -104,7 +114,7 @@ int shard_finalize(og_shard *s, bool scan_snappy) {
     CU(cudaMemcpy(tot, d_tot, 16, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&mx, d_max, 4, cudaMemcpyDeviceToHost));
-    cudaFree(d_types); cudaFree(d_tot); cudaFree(d_max); cudaFree(d_err);
+    dev_free(d_types); dev_free(d_tot); dev_free(d_max); dev_free(d_err);
     if (err[0]) {
         set_error("segment %d: %s page (device validation code %d)", err[1], err[0] == D_UNSUPPORTED ? "unsupported codec in" : err[0] == D_TYPE ? "type mismatch in" : "corrupt", err[0]);
         return map_dev_err(err[0]);
@@ -129,6 +139,11 @@ OG_API int og_init(int device_ordinal) {
     if (device_ordinal < 0 || device_ordinal >= n) { set_error("device ordinal %d out of range (%d devices)", device_ordinal, n); return OG_E_INVAL; }
     CU(cudaSetDevice(device_ordinal));
     CU(cudaFree(0));
+    { /* keep freed buffers in the device's memory pool (see internal.h dev_malloc) */
+        cudaMemPool_t pool; uint64_t thr = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        else cudaGetLastError();
+    }
     g_device = device_ordinal;
     return OG_OK;
 }
@@ -149,7 +164,16 @@ OG_API const char *og_strerror(int st) {
     }
 }
 OG_API const char *og_last_error(void) { return g_err; }
-OG_API const char *og_version(void) { return "ogpu 0.1 (sm_100a)"; }
+OG_API const char *og_version(void) { return "ogpu 0.2 (sm_100a)"; }
+OG_API int og_release_cached_memory(void) {
+    if (g_device < 0) return OG_OK;
+    CU(cudaSetDevice(g_device));
+    CU(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, g_device));
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return OG_OK;
+}
 
 /* =============================================== shard =============================================== */
 } // extern "C"
@@ -165,14 +189,14 @@ extern "C" {
 
 OG_API void og_shard_close(og_shard *s) {
     if (!s) return;
-    if (s->owns_data && s->d_data) cudaFree(s->d_data);
-    cudaFree(s->d_series_seg_begin); cudaFree(s->d_seg_series); cudaFree(s->d_seg_rows); cudaFree(s->d_tmin); cudaFree(s->d_tmax);
-    cudaFree(s->d_page_off); cudaFree(s->d_page_len); cudaFree(s->d_sids);
+    if (s->owns_data && s->d_data) dev_free(s->d_data);
+    dev_free(s->d_series_seg_begin); dev_free(s->d_seg_series); dev_free(s->d_seg_rows); dev_free(s->d_tmin); dev_free(s->d_tmax);
+    dev_free(s->d_page_off); dev_free(s->d_page_len); dev_free(s->d_sids);
     if (s->h_seg_buf) cudaFreeHost(s->h_seg_buf);
-    if (s->d_seg_buf) cudaFree(s->d_seg_buf);
+    if (s->d_seg_buf) dev_free(s->d_seg_buf);
     for (auto &c : s->il) {
-        cudaFree(c.words); cudaFree(c.grp_off); cudaFree(c.grp_rows); cudaFree(c.grp_col); cudaFree(c.ok); cudaFree(c.lane_seg); cudaFree(c.lane_rows);
-        cudaFree(c.lane_series); cudaFree(c.lane_t0); cudaFree(c.lane_dt); cudaFree(c.gen_list);
+        dev_free(c.words); dev_free(c.grp_off); dev_free(c.grp_rows); dev_free(c.grp_col); dev_free(c.ok); dev_free(c.lane_seg); dev_free(c.lane_rows);
+        dev_free(c.lane_series); dev_free(c.lane_t0); dev_free(c.lane_dt); dev_free(c.gen_list);
     }
     delete s;
 }
@@ -295,9 +319,9 @@ OG_API void og_query_destroy(og_query *q) {
     if (!q) return;
     if (q->merge_state) og_query_free_merge_state(q->merge_state);
     free_plan(q->plan);
-    for (void *p : q->scratch) cudaFree(p);
-    for (int c = 0; c < OG_MAX_CALLS; c++) { cudaFree(q->dense[c].val); cudaFree(q->dense[c].ok); cudaFree(q->dense[c].tim); }
-    cudaFree(q->d_group_of_series);
+    for (void *p : q->scratch) dev_free(p);
+    for (int c = 0; c < OG_MAX_CALLS; c++) { dev_free(q->dense[c].val); dev_free(q->dense[c].ok); dev_free(q->dense[c].tim); }
+    dev_free(q->d_group_of_series);
     if (q->ev0) cudaEventDestroy(q->ev0);
     if (q->ev1) cudaEventDestroy(q->ev1);
     for (cudaEvent_t e : q->main_ev) cudaEventDestroy(e);
@@ -444,7 +468,7 @@ void launch_fast(int fm, bool times, bool fold, const IlP &il, uint32_t g0, uint
     return launch_fast_t<63, true>(fold, il, g0, g1, p, ch, st);
 }
 
-struct TmpBufs { std::vector<void *> v; ~TmpBufs() { for (void *p : v) cudaFree(p); } template <class T> int get(T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) v.push_back(*p); return rc; } };
+struct TmpBufs { std::vector<void *> v; ~TmpBufs() { for (void *p : v) dev_free(p); } template <class T> int get(T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) v.push_back(*p); return rc; } };
 
 /* Build (once per shard and column) the lane-interleaved, length-binned stream copy that k_fused_il reads (il_build.cuh).
  * Returns OG_OK with state 1 (ready), -1 (nothing eligible) or -2 (not enough device memory: the general fused kernel
@@ -531,10 +555,10 @@ int ensure_il(og_shard *s, int col, cudaStream_t st) {
     uint64_t total = 0;
     for (uint32_t g = 0; g < ng; g++) { go[g] = total; total += (uint64_t)gw[g] * 32; }
     size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
+    CU(dev_mem_info(&free_b, &total_b));
     size_t headroom = (size_t)8 << 30;
     if (const char *ov = getenv("OGPU_IL_HEADROOM_MB")) headroom = (size_t)atoll(ov) << 20; /* test hook */
-    if (total * 4 + headroom > free_b || cudaMalloc(&ic.words, total * 4) != cudaSuccess) { /* keep room for the query scratch: the general kernel serves the column */
+    if (total * 4 + headroom > free_b || dev_malloc((void **)&ic.words, total * 4) != cudaSuccess) { /* keep room for the query scratch: the general kernel serves the column */
         cudaGetLastError(); ic.words = nullptr; ic.state = -2;
         return OG_OK;
     }
@@ -597,7 +621,7 @@ int build_plan(og_query *q) {
     size_t cell_bytes_per_series = 0;
     for (uint32_t c = 0; c < p.n_calls; c++) cell_bytes_per_series += (size_t)p.n_buckets * (9 + (p.calls[c].func >= OG_AGG_MIN ? 8 : 0));
     size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
+    CU(dev_mem_info(&free_b, &total_b));
     size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
     q->chunk_series = (uint32_t)std::max<size_t>(1, std::min<size_t>(s->n_series, budget / std::max<size_t>(1, cell_bytes_per_series)));
     if (const char *ov = getenv("OGPU_CHUNK_SERIES")) { /* test hook: force small chunks so the multi-chunk paths get exercised */
@@ -658,7 +682,7 @@ int build_plan(og_query *q) {
         /* the decode step is one thread per page: it needs hundreds of thousands of pages in flight to hide latency, so the
          * tile is sized by free memory (a quarter of it, at most 12 GB), not by the L2 */
         size_t fb = 0, tb = 0;
-        CU(cudaMemGetInfo(&fb, &tb));
+        CU(dev_mem_info(&fb, &tb));
         const size_t tile_budget = std::max<size_t>((size_t)96 << 20, std::min<size_t>(fb / 4, (size_t)12 << 30));
         q->tile_segs = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::max<uint32_t>(1, max_chunk_segs), tile_budget / per_seg));
         q->tile_segs = std::max<uint32_t>(32, q->tile_segs & ~31u);
@@ -834,7 +858,7 @@ OG_API int og_query_stats(const og_query *q, og_stats *out) {
         unsigned long long *d_o; int rc = dalloc(&d_o, 3); if (rc) return rc;
         cudaMemset(d_o, 0, 24);
         if (q->sh->n_segments) k_sum_page_bytes<<<(q->sh->n_segments + 255) / 256, 256>>>(make_dir(q->sh), q->qp, q->qp.tmin, q->qp.tmax, d_o);
-        unsigned long long h[3]; CU(cudaMemcpy(h, d_o, 24, cudaMemcpyDeviceToHost)); cudaFree(d_o);
+        unsigned long long h[3]; CU(cudaMemcpy(h, d_o, 24, cudaMemcpyDeviceToHost)); dev_free(d_o);
         mq->stats.page_bytes = h[0]; mq->stats.rows_decoded = h[1]; mq->stats.segments_scanned = h[2];
     }
     *out = q->stats;
@@ -991,7 +1015,7 @@ OG_API int og_decode_column_device(og_shard *s, uint32_t column, uint32_t seg_be
     int type = column == s->n_columns ? OG_TYPE_INT : s->col_types[column];
     uint32_t n = seg_end - seg_begin;
     k_decode_column<<<(n + 127) / 128, 128>>>(make_dir(s), column, type, seg_begin, seg_end, (uint8_t *)d_values, value_stride_bytes, d_rows_out, nullptr, 0, d_err);
-    int err[2]; cudaError_t e = cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost); cudaFree(d_err);
+    int err[2]; cudaError_t e = cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost); dev_free(d_err);
     if (e != cudaSuccess) return cuda_fail(e, "k_decode_column", __FILE__, __LINE__);
     if (err[0]) { set_error("segment %d failed to decode (device code %d)", err[1], err[0]); return map_dev_err(err[0]); }
     return OG_OK;
@@ -1006,9 +1030,9 @@ OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out)
     size_t val_stride = (size_t)R * 8, bm_stride = (((size_t)R + 7) / 8 + 7) & ~(size_t)7;
     size_t need = ncol1 * (val_stride + bm_stride + 16);
     if (s->d_seg_buf_bytes < need) {
-        if (s->d_seg_buf) cudaFree(s->d_seg_buf);
+        if (s->d_seg_buf) dev_free(s->d_seg_buf);
         if (s->h_seg_buf) cudaFreeHost(s->h_seg_buf);
-        CU(cudaMalloc(&s->d_seg_buf, need)); CU(cudaMallocHost(&s->h_seg_buf, need));
+        CU(dev_malloc((void **)&s->d_seg_buf, need)); CU(cudaMallocHost(&s->h_seg_buf, need));
         s->d_seg_buf_bytes = s->h_seg_buf_bytes = need;
     }
     uint8_t *dv = (uint8_t *)s->d_seg_buf, *dbm = dv + ncol1 * val_stride;
@@ -1020,7 +1044,7 @@ OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out)
         int type = c == s->n_columns ? OG_TYPE_INT : s->col_types[c];
         k_decode_column<<<1, 32>>>(dir, c, type, segment, segment + 1, dv + c * val_stride, val_stride, drows + c, dbm + c * bm_stride, (uint32_t)bm_stride, d_err);
     }
-    int err[2]; cudaError_t e = cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost); cudaFree(d_err);
+    int err[2]; cudaError_t e = cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost); dev_free(d_err);
     if (e != cudaSuccess) return cuda_fail(e, "k_decode_column", __FILE__, __LINE__);
     if (err[0]) { set_error("segment %d failed to decode (device code %d)", err[1], err[0]); return map_dev_err(err[0]); }
     CU(cudaMemcpy(s->h_seg_buf, s->d_seg_buf, need, cudaMemcpyDeviceToHost));

@@ -179,11 +179,11 @@ OG_API int og_comm_info(const og_comm *c, int *rank, int *world, int *nccl_versi
 OG_API int og_comm_allreduce_f64(og_comm *c, double *vals, int n, int op_max) {
     if (!c || !vals || n <= 0 || n > 64) return OG_E_INVAL;
     CU(cudaSetDevice(c->device));
-    double *d; CU(cudaMalloc(&d, (size_t)n * 8));
+    double *d; CU(dev_malloc((void **)&d, (size_t)n * 8));
     CU(cudaMemcpy(d, vals, (size_t)n * 8, cudaMemcpyHostToDevice));
     ncclResult_t r = g_nccl.AllReduce(d, d, (size_t)n, ncclFloat64, op_max ? ncclMax : ncclSum, c->comm, nullptr);
     cudaError_t e = cudaMemcpy(vals, d, (size_t)n * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d);
+    dev_free(d);
     if (r != ncclSuccess) { set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); return OG_E_CUDA; }
     if (e != cudaSuccess) return cuda_fail(e, "allreduce copy", __FILE__, __LINE__);
     return OG_OK;
@@ -192,7 +192,7 @@ OG_API int og_comm_allreduce_f64(og_comm *c, double *vals, int n, int op_max) {
 static void merge_state_free(og_merge_state *ms) {
     if (!ms) return;
     if (ms->graph) cudaGraphExecDestroy(ms->graph);
-    for (void *p : ms->bufs) cudaFree(p);
+    for (void *p : ms->bufs) dev_free(p);
     delete ms;
 }
 void og_query_free_merge_state(void *p) { merge_state_free((og_merge_state *)p); }
@@ -233,11 +233,11 @@ OG_API int og_query_allreduce(og_query *q, og_comm *c) {
             else if (mc.func == OG_AGG_SUM || mc.func == OG_AGG_COUNT) { mc.kind = 1; mc.slot = m.n_i64++; }
             else { mc.kind = 2; mc.slot = m.n_sel++; }
         }
-        if (m.n_f64) { CU(cudaMalloc(&ms->bufs[0], (size_t)m.n_f64 * m.cells * 8)); m.f64 = (double *)ms->bufs[0]; }
-        if (m.n_f64 + m.n_i64) { CU(cudaMalloc(&ms->bufs[1], (size_t)(2 * m.n_i64 + m.n_f64) * m.cells * 8)); m.i64 = (int64_t *)ms->bufs[1]; }
+        if (m.n_f64) { CU(dev_malloc((void **)&ms->bufs[0], (size_t)m.n_f64 * m.cells * 8)); m.f64 = (double *)ms->bufs[0]; }
+        if (m.n_f64 + m.n_i64) { CU(dev_malloc((void **)&ms->bufs[1], (size_t)(2 * m.n_i64 + m.n_f64) * m.cells * 8)); m.i64 = (int64_t *)ms->bufs[1]; }
         if (m.n_sel) {
-            CU(cudaMalloc(&ms->bufs[2], (size_t)m.n_sel * 3 * m.cells * 8)); m.sel_send = (uint64_t *)ms->bufs[2];
-            CU(cudaMalloc(&ms->bufs[3], (size_t)m.world * m.n_sel * 3 * m.cells * 8)); m.sel_recv = (uint64_t *)ms->bufs[3];
+            CU(dev_malloc((void **)&ms->bufs[2], (size_t)m.n_sel * 3 * m.cells * 8)); m.sel_send = (uint64_t *)ms->bufs[2];
+            CU(dev_malloc((void **)&ms->bufs[3], (size_t)m.world * m.n_sel * 3 * m.cells * 8)); m.sel_recv = (uint64_t *)ms->bufs[3];
         }
     }
     if (!ms->geometry_checked) { /* every rank must hold the same grid and the same calls: compare a fingerprint through the communicator */

@@ -414,7 +414,7 @@ __global__ void k_synth_times(og_synth_desc d, uint32_t seg_begin, uint32_t n_se
 
 template <class T> static int dalloc2(T **p, size_t n) {
     *p = nullptr;
-    cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(1, n) * sizeof(T));
+    cudaError_t e = dev_malloc((void **)p, std::max<size_t>(1, n) * sizeof(T));
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? OG_E_NOMEM : OG_E_CUDA; }
     return OG_OK;
 }
@@ -435,8 +435,8 @@ OG_API int og_encode_pages(int32_t type, int32_t is_time, const void *d_values, 
     uint8_t *staging; uint64_t *dense = nullptr; int *flags; unsigned long long *d_total;
     int rc;
     if ((rc = dalloc2(&staging, (size_t)n_segments * PAGE_STRIDE))) return rc;
-    if (type == OG_TYPE_INT && d_valid && !is_time && (rc = dalloc2(&dense, (size_t)n_segments * rps))) { cudaFree(staging); return rc; }
-    if ((rc = dalloc2(&flags, 1)) || (rc = dalloc2(&d_total, 1))) { cudaFree(staging); cudaFree(dense); return rc; }
+    if (type == OG_TYPE_INT && d_valid && !is_time && (rc = dalloc2(&dense, (size_t)n_segments * rps))) { dev_free(staging); return rc; }
+    if ((rc = dalloc2(&flags, 1)) || (rc = dalloc2(&d_total, 1))) { dev_free(staging); dev_free(dense); return rc; }
     cudaMemset(flags, 0, 4);
     k_encode_pages<<<(n_segments + 63) / 64, 64>>>(type, is_time, (const uint8_t *)d_values, is_time ? nullptr : d_valid, d_rows, n_segments, rps, staging, d_page_len, dense, flags);
     k_scan_lens<<<1, 1024>>>(d_page_len, n_segments, 0, d_page_off, d_total);
@@ -444,7 +444,7 @@ OG_API int og_encode_pages(int32_t type, int32_t is_time, const void *d_values, 
     unsigned long long total = 0; int fl = 0;
     cudaError_t e = cudaMemcpy(&total, d_total, 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(&fl, flags, 4, cudaMemcpyDeviceToHost);
-    cudaFree(staging); cudaFree(dense); cudaFree(flags); cudaFree(d_total);
+    dev_free(staging); dev_free(dense); dev_free(flags); dev_free(d_total);
     if (e != cudaSuccess) return cuda_fail(e, "og_encode_pages", __FILE__, __LINE__);
     if (fl & 2) { set_error("float column contains +Inf and -Inf (or NaN): FloatArrayEncodeAll rejects it (batch_float.go:245)"); return OG_E_INVAL; }
     if (fl & 16) { set_error("output buffer too small (%llu bytes needed)", total); return OG_E_NOMEM; }
@@ -484,7 +484,7 @@ OG_API int og_shard_synth(const og_synth_desc *dd, og_shard **out) {
     /* batch scratch */
     uint32_t batch = std::min<uint32_t>(nseg, 128u * 1024u);
     uint8_t *cells, *okb, *staging; uint32_t *rows_arr, *lens; uint64_t *offs, *dense; int *flags; unsigned long long *d_total;
-    struct Guard { std::vector<void *> p; ~Guard() { for (void *x : p) cudaFree(x); } } guard;
+    struct Guard { std::vector<void *> p; ~Guard() { for (void *x : p) dev_free(x); } } guard;
 #define GALLOC(ptr, n) do { STRY(dalloc2(&ptr, n)); guard.p.push_back(ptr); } while (0)
     GALLOC(cells, (size_t)batch * rps * 8); GALLOC(okb, (size_t)batch * rps); GALLOC(staging, (size_t)batch * PAGE_STRIDE);
     GALLOC(rows_arr, batch); GALLOC(lens, batch); GALLOC(offs, batch); GALLOC(dense, (size_t)batch * rps); GALLOC(flags, 1); GALLOC(d_total, 1);

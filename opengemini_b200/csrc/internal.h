@@ -20,6 +20,15 @@ namespace ogpu {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int ensure_device(); /* bind the calling thread to the library's device (og_init(0) on first use) */
+
+/* Device memory comes from the device's stream-ordered pool (cudaMallocAsync on the legacy stream) with its release threshold
+ * raised at og_init: shards and queries that are opened and closed in a loop get their buffers back from the pool instead of
+ * paying cudaMalloc/cudaFree (tens of ms per GB-sized buffer) every time.  Every buffer is released only after the stream that
+ * used it has been synchronised (og_query_run / og_shard_open return synchronised), so reuse across streams is ordered. */
+inline cudaError_t dev_malloc(void **p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t)0); }
+inline void dev_free(void *p) { if (p) cudaFreeAsync(p, (cudaStream_t)0); }
+/* free device memory as a budget sees it: what the driver reports plus what the pool holds but does not use */
+cudaError_t dev_mem_info(size_t *free_b, size_t *total_b);
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ::ogpu::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
 
 struct DevBuf { /* RAII-less helper: explicit free */
