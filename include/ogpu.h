@@ -203,7 +203,8 @@ typedef struct og_stats {
     double h2d_ms;
     double main_kernel_ms;     /* of which: the dominant decode+reduce kernel(s) (k_fused_segment, or decode/filter/reduce tiles) */
     uint32_t kernel_launches;  /* kernels launched by the last og_query_run */
-    int32_t path;              /* 0 generic materialise-tile path; 1 fused, general per-segment kernel only; 2 fused Gorilla kernel over the
+    int32_t path;              /* 0 generic materialise-tile path; 4 fused multi-column / WHERE kernel (pull iterators, nothing
+                                  materialised); 1 fused, general per-segment kernel only; 2 fused Gorilla kernel over the
                                   lane-interleaved copy with per-series cells (strict order / tag groups / per-series output);
                                   3 the same with interior windows folded in-warp (one tagset, regular shard) */
     int32_t il_state;          /* lane-interleaved copy of the queried float column: 1 ready, 0 not applicable, -1 no eligible page,

@@ -11,6 +11,7 @@
 #include "agg_kernels.cuh"
 #include "fused.cuh"
 #include "il_build.cuh"
+#include "fused_multi.cuh"
 #include "snappy_load.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -429,6 +430,7 @@ namespace {
 struct Plan { /* built once per query, reused by every og_query_run */
     ChunkP ch; TileP tp; GroupP gp;
     bool fused;
+    bool multi;     /* several columns and/or a WHERE: pull-iterator kernel k_fused_multi, nothing materialised */
     bool fast;      /* the fused Gorilla kernel serves the eligible segments, k_fused_segment the rest */
     bool fold;      /* interior windows are folded in-warp into gcells (one tagset, regular shard, no strict order) */
     int fm; bool times;
@@ -609,7 +611,8 @@ int build_plan(og_query *q) {
     for (uint32_t c = 0; c < p.n_calls; c++) pl->gp.dense[c] = q->dense[c];
 
     pl->fused = p.n_cols == 1 && p.n_filter == 0 && !(q->desc.flags & OG_Q_NO_FUSED);
-    q->path_used = pl->fused ? 1 : 0;
+    pl->multi = !pl->fused && p.n_cols <= OG_MULTI_MAXC && !(q->desc.flags & OG_Q_NO_FUSED);
+    q->path_used = pl->fused ? 1 : pl->multi ? 4 : 0;
     const bool want_fast = pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments;
     if (want_fast && (rc = ensure_il(s, p.col_index[0], st))) return rc;
     pl->fast = want_fast && s->il[p.col_index[0]].state == 1;
@@ -675,7 +678,7 @@ int build_plan(og_query *q) {
         pl->fm |= FM_COUNT; /* the row count also is the validity of every partial */
         q->path_used = pl->fold ? 3 : 2;
     }
-    if (!pl->fused) { /* generic path: materialisation tile */
+    if (!pl->fused && !pl->multi) { /* generic path: materialisation tile */
         TileP &tp = pl->tp;
         tp.R = std::max<uint32_t>(1, s->max_seg_rows);
         size_t per_seg = (size_t)tp.R * (p.n_cols * 9 + 8 + 1);
@@ -772,6 +775,15 @@ OG_API int og_query_run(og_query *q) {
                 }
                 launches++;
             }
+        } else if (pl->multi) {
+            const unsigned gb = (nseg + 127) / 128;
+            switch (p.n_cols) {
+            case 1: k_fused_multi<1><<<gb, 128, 0, st>>>(dir, p, ch); break;
+            case 2: k_fused_multi<2><<<gb, 128, 0, st>>>(dir, p, ch); break;
+            case 3: k_fused_multi<3><<<gb, 128, 0, st>>>(dir, p, ch); break;
+            default: k_fused_multi<4><<<gb, 128, 0, st>>>(dir, p, ch); break;
+            }
+            launches++;
         } else {
             for (uint32_t t0 = ch.seg_begin; t0 < ch.seg_end; t0 += q->tile_segs) {
                 tp.tile_begin = t0; tp.tile_end = std::min(ch.seg_end, t0 + q->tile_segs);

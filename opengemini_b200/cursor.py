@@ -266,13 +266,31 @@ class Comm:
         self.h, self.rank, self.world = handle, rank, world
 
     @staticmethod
+    def _prefer_bundled_nccl():
+        """libogpu dlopens "libnccl.so.2".  When PyTorch is installed it ships its own copy under the same SONAME; whichever is
+        loaded first serves the whole process, and an older system copy loaded first breaks a later `import torch`.  Point
+        OGPU_NCCL_LIB at the bundled one (no torch import needed) unless the caller chose a library."""
+        import importlib.util
+        import os
+        if os.environ.get("OGPU_NCCL_LIB"):
+            return
+        spec = importlib.util.find_spec("nvidia.nccl") if importlib.util.find_spec("nvidia") else None
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["OGPU_NCCL_LIB"] = cand
+                return
+
+    @staticmethod
     def unique_id():
+        Comm._prefer_bundled_nccl()
         buf = (C.c_uint8 * 128)()
         L.check(L.lib().og_comm_unique_id(buf), "og_comm_unique_id")
         return bytes(buf)
 
     @classmethod
     def init_rank(cls, uid, rank, world):
+        cls._prefer_bundled_nccl()
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         h = C.c_void_p()
         L.check(L.lib().og_comm_init_rank(buf, int(rank), int(world), C.byref(h)), "og_comm_init_rank")
