@@ -461,6 +461,42 @@ __global__ void k_merge_per_series(QueryP q, ChunkP ch, GroupP gp) {
     store_part(gp.dense[c], (size_t)ch.series_begin * q.n_buckets + i, a);
 }
 
+/* one tagset, order not pinned (no OG_Q_STRICT_ORDER): the per-series cells of a block of OG_MERGE_SB consecutive series are
+ * folded in series order by one thread per bucket (coalesced across buckets), and the block partials go to the folded cell
+ * matrix (column = block) that k_merge_folded reduces — thousands of threads instead of one per bucket when a shard has many
+ * series and few buckets. */
+#define OG_MERGE_SB 256u
+__global__ void __launch_bounds__(128) k_merge_all_blocks(QueryP q, ChunkP ch, GroupP gp) {
+    if (ch.flags[0] == 0) return; /* no per-series cell was written */
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x, blk = blockIdx.y, c = blockIdx.z;
+    if (b >= q.n_buckets) return;
+    const uint32_t nS = ch.series_end - ch.series_begin;
+    const uint32_t s0 = blk * OG_MERGE_SB, s1 = min(nS, s0 + OG_MERGE_SB);
+    const int func = q.calls[c].func, ftype = call_ftype(q, c);
+    const bool multi = q.multi != 0;
+    const Tri cells = ch.cells[c];
+    Part acc = part_empty();
+    constexpr int U = 8;
+    for (uint32_t s = s0; s < s1; s += U) {
+        uint32_t okv[U]; uint64_t vv[U]; int64_t tt[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool in = s + u < s1;
+            const size_t ci = in ? (size_t)(s + u) * ch.nb + b : 0;
+            okv[u] = in ? cells.ok[ci] : 0;
+            vv[u] = okv[u] ? cells.val[ci] : 0;
+            tt[u] = (okv[u] && cells.tim) ? cells.tim[ci] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!okv[u]) continue;
+            Part p; p.ok = 1; p.v = vv[u]; p.t = tt[u];
+            group_update(func, ftype, multi, acc, p);
+        }
+    }
+    if (acc.ok) store_part(ch.gcells[c], (size_t)b * ch.gc_cols + blk, acc);
+}
+
 /* one tagset: dense[b] (+)= fold over the columns of the folded cell matrix (warp per bucket, grid.y = call; lanes take
  * columns lane, lane+32, ... in order, then a butterfly: a fixed association, so results are reproducible run to run) */
 __global__ void k_merge_folded(QueryP q, ChunkP ch, GroupP gp) {

@@ -432,6 +432,7 @@ struct Plan { /* built once per query, reused by every og_query_run */
     bool fused;
     bool multi;     /* several columns and/or a WHERE: pull-iterator kernel k_fused_multi, nothing materialised */
     bool fast;      /* the fused Gorilla kernel serves the eligible segments, k_fused_segment the rest */
+    bool blockmerge;/* one tagset, order not pinned, per-series cells: two-stage parallel merge (k_merge_all_blocks + k_merge_folded) */
     bool fold;      /* interior windows are folded in-warp into gcells (one tagset, regular shard, no strict order) */
     int fm; bool times;
     IlP il;
@@ -468,6 +469,34 @@ void launch_fast(int fm, bool times, bool fold, const IlP &il, uint32_t g0, uint
         }
     }
     return launch_fast_t<63, true>(fold, il, g0, g1, p, ch, st);
+}
+
+template <int NCOL, int NCALL> void launch_multi_t(const QueryP &p, const DirP &d, const ChunkP &ch, uint32_t nseg, cudaStream_t st) {
+    bool simple = true;
+    for (uint32_t c = 0; c < p.n_calls; c++) simple &= p.calls[c].func == OG_AGG_COUNT || p.calls[c].func == OG_AGG_SUM;
+    const unsigned gb = (nseg + 127) / 128;
+    if (simple) k_fused_multi<NCOL, NCALL, true><<<gb, 128, 0, st>>>(d, p, ch);
+    else k_fused_multi<NCOL, NCALL, false><<<gb, 128, 0, st>>>(d, p, ch);
+}
+template <int NCOL> void launch_multi_c(const QueryP &p, const DirP &d, const ChunkP &ch, uint32_t nseg, cudaStream_t st) {
+    switch (p.n_calls) {
+    case 1: return launch_multi_t<NCOL, 1>(p, d, ch, nseg, st);
+    case 2: return launch_multi_t<NCOL, 2>(p, d, ch, nseg, st);
+    case 3: return launch_multi_t<NCOL, 3>(p, d, ch, nseg, st);
+    case 4: return launch_multi_t<NCOL, 4>(p, d, ch, nseg, st);
+    case 5: return launch_multi_t<NCOL, 5>(p, d, ch, nseg, st);
+    case 6: return launch_multi_t<NCOL, 6>(p, d, ch, nseg, st);
+    case 7: return launch_multi_t<NCOL, 7>(p, d, ch, nseg, st);
+    default: return launch_multi_t<NCOL, 8>(p, d, ch, nseg, st);
+    }
+}
+void launch_multi(const QueryP &p, const DirP &d, const ChunkP &ch, uint32_t nseg, cudaStream_t st) {
+    switch (p.n_cols) {
+    case 1: return launch_multi_c<1>(p, d, ch, nseg, st);
+    case 2: return launch_multi_c<2>(p, d, ch, nseg, st);
+    case 3: return launch_multi_c<3>(p, d, ch, nseg, st);
+    default: return launch_multi_c<4>(p, d, ch, nseg, st);
+    }
 }
 
 struct TmpBufs { std::vector<void *> v; ~TmpBufs() { for (void *p : v) dev_free(p); } template <class T> int get(T **p, size_t n) { int rc = dalloc(p, n); if (rc == OG_OK) v.push_back(*p); return rc; } };
@@ -656,6 +685,19 @@ int build_plan(og_query *q) {
         if (sel && (rc = salloc(q, &ch.edges[c].tim, 2 * (size_t)max_chunk_segs))) return rc;
     }
     if ((rc = salloc(q, &ch.edge_bucket, 2 * (size_t)max_chunk_segs))) return rc;
+    pl->blockmerge = !pl->fold && q->desc.group_mode == OG_GROUP_ALL && !(q->desc.flags & OG_Q_STRICT_ORDER) &&
+                     (s->n_series > 2 * OG_MERGE_SB || getenv("OGPU_FORCE_BLOCKMERGE") /* test hook */);
+    if (pl->blockmerge) { /* block partials of the two-stage merge live in the folded cell matrix: one column per block of series */
+        ch.gc_edge0 = 0; ch.gc_col0 = 0;
+        ch.gc_cols = (std::min(q->chunk_series, s->n_series) + OG_MERGE_SB - 1) / OG_MERGE_SB;
+        const size_t n = (size_t)p.n_buckets * ch.gc_cols;
+        for (uint32_t c = 0; c < p.n_calls; c++) {
+            bool sel = p.calls[c].func >= OG_AGG_MIN;
+            if ((rc = salloc(q, &ch.gcells[c].val, n))) return rc;
+            if ((rc = salloc(q, &ch.gcells[c].ok, n))) return rc;
+            if (sel && (rc = salloc(q, &ch.gcells[c].tim, n))) return rc;
+        }
+    }
     if (pl->fold) { /* folded cell matrix: lane-group columns, then one column per block of 32 consecutive series (stitched edge windows) */
         ch.gc_edge0 = ic->n_super * ic->cols_per_super; ch.gc_col0 = 0;
         ch.gc_cols = ch.gc_edge0 + (s->n_series + 31) / 32;
@@ -746,7 +788,7 @@ OG_API int og_query_run(og_query *q) {
         segs_scanned += nseg;
         if (clear_cells) for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.cells[c].ok, 0, chunk_cells, st));
         /* folded cells are per chunk: a lane group that straddles chunks contributes to its column once per chunk */
-        if (pl->fold) for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.gcells[c].ok, 0, (size_t)p.n_buckets * ch.gc_cols, st));
+        if (pl->fold || pl->blockmerge) for (uint32_t c = 0; c < p.n_calls; c++) CU(cudaMemsetAsync(ch.gcells[c].ok, 0, (size_t)p.n_buckets * ch.gc_cols, st));
         CU(cudaEventRecord(q->main_ev[2 * chunks_run], st));
         if (pl->fused) {
             const uint32_t *gl = nullptr; uint32_t gn = nseg;
@@ -776,13 +818,7 @@ OG_API int og_query_run(og_query *q) {
                 launches++;
             }
         } else if (pl->multi) {
-            const unsigned gb = (nseg + 127) / 128;
-            switch (p.n_cols) {
-            case 1: k_fused_multi<1><<<gb, 128, 0, st>>>(dir, p, ch); break;
-            case 2: k_fused_multi<2><<<gb, 128, 0, st>>>(dir, p, ch); break;
-            case 3: k_fused_multi<3><<<gb, 128, 0, st>>>(dir, p, ch); break;
-            default: k_fused_multi<4><<<gb, 128, 0, st>>>(dir, p, ch); break;
-            }
+            launch_multi(p, dir, ch, nseg, st);
             launches++;
         } else {
             for (uint32_t t0 = ch.seg_begin; t0 < ch.seg_end; t0 += q->tile_segs) {
@@ -801,9 +837,10 @@ OG_API int og_query_run(og_query *q) {
         if (pl->fold) k_fix_edges_fold<<<(unsigned)(((size_t)((b - a + 31) / 32) * ch.J * 32 + 127) / 128), 128, 0, st>>>(dir, p, ch);
         else k_fix_edges<<<(nseg + 127) / 128, 128, 0, st>>>(dir, p, ch);
         if (per_series) k_merge_per_series<<<dim3((unsigned)((chunk_cells + 255) / 256), p.n_calls), 256, 0, st>>>(p, ch, gp);
+        else if (pl->blockmerge) k_merge_all_blocks<<<dim3((p.n_buckets + 127) / 128, (b - a + OG_MERGE_SB - 1) / OG_MERGE_SB, p.n_calls), 128, 0, st>>>(p, ch, gp);
         else k_merge_groups<<<dim3((unsigned)((cells_dense + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp); /* returns at once when no per-series cell was written */
         launches += 2;
-        if (pl->fold) { k_merge_folded<<<dim3((unsigned)(((size_t)p.n_buckets * 32 + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp); launches++; }
+        if (pl->fold || pl->blockmerge) { k_merge_folded<<<dim3((unsigned)(((size_t)p.n_buckets * 32 + 127) / 128), p.n_calls), 128, 0, st>>>(p, ch, gp); launches++; }
     }
     CU(cudaEventRecord(q->ev1, st));
     CU(cudaGetLastError());

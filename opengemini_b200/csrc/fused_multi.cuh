@@ -97,12 +97,13 @@ struct ColIter {
         case K_F_SAME: return cur;
         case K_F_GORILLA: {
             if (i == 0) return cur;
-            /* one record of tsm1.FloatArrayDecodeAll (batch_float.go:352-508) */
+            /* one record of tsm1.FloatArrayDecodeAll (batch_float.go:352-508).  '0' (same value) and '10' (window reuse) are
+             * handled without a branch — a '0' is a record with zero meaningful bits — so lanes of a warp that sit on different
+             * record kinds do not serialise; only the rare '11' (new window) branches. */
             const uint8_t *bp = p + (aux >> 3);
             const unsigned sh = (unsigned)(aux & 7);
-            uint64_t w = ld_be64(bp) << sh; /* >= 57 valid bits */
-            if (!(w >> 63)) { aux += 1; if (aux > c) err = D_CORRUPT; return cur; }
-            unsigned used = 2;
+            const uint64_t w = ld_be64(bp) << sh; /* >= 57 valid bits */
+            unsigned used = (w >> 63) ? 2u : 1u;
             if ((w >> 62) == 3) {
                 const unsigned lm = (unsigned)(w >> 51) & 0x7ff;
                 const unsigned lead = (lm >> 6) & 0x1f;
@@ -111,17 +112,17 @@ struct ColIter {
                 else { a = 0; b = 64; }
                 used = 13;
             }
+            const unsigned mb = (w >> 63) ? b : 0u; /* meaningful bits of this record */
             aux += used;
-            /* b meaningful bits at bit position aux */
             const uint8_t *q2 = p + (aux >> 3);
             const unsigned s2 = (unsigned)(aux & 7);
             uint64_t v = ld_be64(q2) << s2;
-            if (s2 && s2 + b > 64) v |= (uint64_t)__ldg(q2 + 8) >> (8 - s2);
-            v = b == 64 ? v : (v >> (64 - b));
-            aux += b;
+            if (s2 + mb > 64) v |= (uint64_t)__ldg(q2 + 8) >> (8 - s2);
+            v = mb == 64 ? v : mb == 0 ? 0ull : (v >> (64 - mb));
+            aux += mb;
             if (aux > c) { err = D_CORRUPT; return cur; }
             cur ^= v << a;
-            if (cur == OG_UVNAN) err = D_CORRUPT; /* sentinel before the block's value count */
+            if (mb && cur == OG_UVNAN) err = D_CORRUPT; /* sentinel before the block's value count */
             return cur; }
         case K_F_RLE: {
             if (a == 0) { /* next run: [u16 BE n (bit15 = zero run)][8 B LE] */
@@ -161,7 +162,9 @@ struct ColIter {
     }
 };
 
-template <int NCOL>
+/* NCALL = number of calls (partials live in registers); SIMPLE = every call is count or sum (the shape configs[2] names): the
+ * per-call switch of acc_row collapses to an add */
+template <int NCOL, int NCALL, bool SIMPLE>
 __global__ void __launch_bounds__(128) k_fused_multi(DirP d, QueryP q, ChunkP ch) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t seg = ch.seg_begin + i;
@@ -182,12 +185,13 @@ __global__ void __launch_bounds__(128) k_fused_multi(DirP d, QueryP q, ChunkP ch
         col[k].init(d.data + d.page_off[pi], d.page_len[pi], q.col_type[k], rows);
         if (col[k].err != D_OK) { report_err(ch.err, col[k].err, seg); no_rows(); return; }
     }
-    Part parts[OG_MAX_CALLS];
+    Part parts[NCALL];
     uint32_t cur_b = OG_NO_BUCKET, head_b = OG_NO_BUCKET; bool head_done = false;
     int64_t we = 0;
     auto flush = [&](bool final) {
         if (cur_b == OG_NO_BUCKET) return;
-        for (uint32_t c = 0; c < q.n_calls; c++) {
+#pragma unroll
+        for (int c = 0; c < NCALL; c++) {
             if (!head_done) store_part(ch.edges[c], e, parts[c]);
             else if (final) store_part(ch.edges[c], e + 1, parts[c]);
             else if (parts[c].ok) store_cell(ch, (int)c, series, cur_b, parts[c]);
@@ -207,10 +211,15 @@ __global__ void __launch_bounds__(128) k_fused_multi(DirP d, QueryP q, ChunkP ch
             if (cur_b >= q.n_buckets) { report_err(ch.err, D_CORRUPT, seg); cur_b = OG_NO_BUCKET; break; } /* cannot happen on a validated shard */
             we = q.start + (int64_t)(cur_b + 1) * q.interval;
 #pragma unroll
-            for (uint32_t c = 0; c < OG_MAX_CALLS; c++) parts[c] = part_empty();
+            for (int c = 0; c < NCALL; c++) parts[c] = part_empty();
         }
         bool keep = true;
-        if (q.n_filter) { /* RPN over compare terms; a NULL cell never matches (SURVEY App.B.12) */
+        if (q.n_filter == 1) { /* one compare term: no stack machine */
+            const FilterP &f = q.filter[0];
+            keep = false;
+#pragma unroll
+            for (int k = 0; k < NCOL; k++) if (f.col_slot == k) keep = ok[k] && term_pass(f, v[k]);
+        } else if (q.n_filter) { /* RPN over compare terms; a NULL cell never matches (SURVEY App.B.12) */
             uint32_t stack = 0; int sp = 0;
             for (uint32_t fi = 0; fi < q.n_filter; fi++) {
                 const FilterP &f = q.filter[fi];
@@ -229,11 +238,18 @@ __global__ void __launch_bounds__(128) k_fused_multi(DirP d, QueryP q, ChunkP ch
         }
         if (!keep) continue;
 #pragma unroll
-        for (uint32_t c = 0; c < OG_MAX_CALLS; c++) {
-            if (c >= q.n_calls) break;
+        for (int c = 0; c < NCALL; c++) {
             const CallP &cp = q.calls[c];
 #pragma unroll
-            for (int k = 0; k < NCOL; k++) if (cp.col_slot == k && ok[k]) acc_row(cp.func, cp.type, parts[c], v[k], t);
+            for (int k = 0; k < NCOL; k++) {
+                if (cp.col_slot != k || !ok[k]) continue;
+                if (SIMPLE) { /* count: += 1; sum: sequential add in row order (integerSumReduce / floatSumReduce) */
+                    if (cp.func == OG_AGG_COUNT) parts[c].v += 1;
+                    else if (cp.type == OG_TYPE_FLOAT) parts[c].v = d2u(u2d(parts[c].v) + u2d(v[k]));
+                    else parts[c].v += v[k];
+                    parts[c].ok = 1;
+                } else acc_row(cp.func, cp.type, parts[c], v[k], t);
+            }
         }
     }
     for (int k = 0; k < NCOL; k++) if (col[k].err != D_OK) report_err(ch.err, col[k].err, seg);

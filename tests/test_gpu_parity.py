@@ -577,3 +577,23 @@ def test_folded_path_selectors_and_ties():
         run_both(sh, sd, [(f, 0) for f in ALL6], iv, T0, tmax, f"ties multi iv={iv}")
     run_both(sh, sd, [("max", 0), ("count", 0)], 60 * SEC, T0 + 500 * SEC + 3, T0 + 1500 * SEC, "ties mid-range")
     sh.close()
+
+
+def test_two_stage_merge_of_per_series_cells(monkeypatch):
+    """One tagset, order not pinned, per-series cells (multi-column / WHERE queries, general codecs): the cells are folded by
+    blocks of series in parallel and the block partials by k_merge_folded.  OGPU_FORCE_BLOCKMERGE enables it below its size
+    threshold.  Everything but float sums is bitwise; float sums within 1e-12."""
+    monkeypatch.setenv("OGPU_FORCE_BLOCKMERGE", "1")
+    cols = [(L.TYPE_FLOAT, L.SYNTH_F_HI, 30), (L.TYPE_INT, L.SYNTH_INT_WALK, 0), (L.TYPE_BOOL, L.SYNTH_BOOL, 100)]
+    n_series, rows = 700, 3000
+    sh = Shard.synth(n_series, rows, cols, t0=T0, dt=SEC, seed=9)
+    hs = oracle.HostShard(n_series, rows, cols, t0=T0, dt=SEC, seed=9, threads=4)
+    tmax = T0 + (rows - 1) * SEC
+    cases = [([("count", 1), ("sum", 1), ("sum", 0), ("count", 2)], [("term", 0, ">", 100.5)]),
+             ([(f, 0) for f in ALL6], None), ([("max", 1)], [("term", 2, "=", 1)]), ([("first", 0)], None), ([("last", 1), ("min", 0)], None)]
+    for calls, flt in cases:
+        q = AggQuery(sh, calls, 60 * SEC, T0, tmax, filter=flt).run()
+        ref = oracle.scan(hs.desc, q.desc, threads=1)
+        compare_dense(q.dense_host(), ref, calls, len(calls) > 1, f"blockmerge {calls}", float_sum_exact=False)
+        q.close()
+    sh.close()
