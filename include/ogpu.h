@@ -266,6 +266,10 @@ OG_API int og_query_allreduce(og_query *q, og_comm *c);
 
 /* ---- materialise path (KeyCursor.Next for non-aggregating callers) ---- */
 OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out);
+/* flags: OG_DECODE_DESCENDING hands the segment over reversed — values, validity bits and times — as a descending scan does
+ * (reader.go:516-519,1035-1042); callers walk the segments of a series from the last to the first (location.go:137-140,221-232) */
+enum { OG_DECODE_DESCENDING = 1u << 0 };
+OG_API int og_decode_segment_ex(og_shard *s, uint32_t segment, uint32_t flags, og_record_view *out);
 /* decode a range of segments of one column into caller-provided DEVICE buffers (dense values, 8 B or 1 B each);
  * rows_out[i] receives the non-null value count of segment seg_begin+i. column == n_columns selects time. */
 OG_API int og_decode_column_device(og_shard *s, uint32_t column, uint32_t seg_begin, uint32_t seg_end,

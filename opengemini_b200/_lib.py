@@ -98,7 +98,7 @@ class ShardLayout(C.Structure):
 EXPORTS = [
     "og_init", "og_device_count", "og_strerror", "og_last_error", "og_version", "og_shard_open", "og_shard_close",
     "og_shard_info", "og_query_create", "og_query_run", "og_query_next", "og_query_dense", "og_query_stats",
-    "og_query_abort", "og_query_destroy", "og_query_merge_dense", "og_decode_segment", "og_decode_column_device",
+    "og_query_abort", "og_query_destroy", "og_query_merge_dense", "og_decode_segment", "og_decode_segment_ex", "og_decode_column_device",
     "og_shard_synth", "og_shard_layout_get", "og_shard_export", "og_encode_pages",
     "og_release_cached_memory", "og_comm_unique_id", "og_comm_init_rank", "og_comm_destroy", "og_comm_info", "og_comm_allreduce_f64", "og_query_allreduce",
 ]
@@ -142,6 +142,7 @@ def lib():
     L.og_query_destroy.restype = None
     L.og_query_merge_dense.argtypes = [C.c_void_p, C.POINTER(DenseView)]
     L.og_decode_segment.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RecordView)]
+    L.og_decode_segment_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(RecordView)]
     L.og_decode_column_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
     L.og_shard_synth.argtypes = [C.POINTER(SynthDesc), C.POINTER(C.c_void_p)]
     L.og_shard_layout_get.argtypes = [C.c_void_p, C.POINTER(ShardLayout)]

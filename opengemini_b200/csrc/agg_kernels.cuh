@@ -106,6 +106,7 @@ __global__ void k_validate(DirP d, const int32_t *col_types, uint32_t *seg_rows,
                 if (ty == OG_TYPE_FLOAT) rc = (tag == 0 || tag == 3 || tag == 4 || tag == 5) ? D_OK : (tag == 1 || tag == 2 || tag == 6) ? D_UNSUPPORTED : D_CORRUPT;
                 else if (ty == OG_TYPE_INT) rc = (tag == 1 || tag == 2 || tag == 4) ? D_OK : tag == 3 ? D_UNSUPPORTED : D_CORRUPT;
                 else if (ty == OG_TYPE_BOOL) rc = tag == 1 ? D_OK : D_CORRUPT;
+                else if (ty == OG_TYPE_STRING) rc = D_OK; /* only the header (row count, null bitmap) of a string page is ever read: count() */
                 else rc = D_UNSUPPORTED;
             }
         }

@@ -215,8 +215,8 @@ OG_API int og_shard_open(const og_shard_desc *d, og_shard **out) {
     for (uint32_t c = 0; c < d->n_columns; c++) {
         s->col_types.push_back(d->columns[c].type);
         s->col_names.push_back(d->columns[c].name ? d->columns[c].name : "");
-        if (d->columns[c].type != OG_TYPE_INT && d->columns[c].type != OG_TYPE_FLOAT && d->columns[c].type != OG_TYPE_BOOL) {
-            set_error("column %u: type %d is not decodable on the GPU path (strings are out of scope)", c, d->columns[c].type); delete s; return OG_E_UNSUPPORTED;
+        if (d->columns[c].type != OG_TYPE_INT && d->columns[c].type != OG_TYPE_FLOAT && d->columns[c].type != OG_TYPE_BOOL && d->columns[c].type != OG_TYPE_STRING) {
+            set_error("column %u: unknown column type %d", c, d->columns[c].type); delete s; return OG_E_UNSUPPORTED;
         }
     }
     s->sids.assign(d->sids, d->sids + d->n_series);
@@ -363,6 +363,7 @@ OG_API int og_query_create(og_shard *s, const og_query_desc *d_in, og_query **ou
         const og_call &c = d->calls[i];
         if (c.column < 0 || (uint32_t)c.column >= s->n_columns || c.func < OG_AGG_COUNT || c.func > OG_AGG_LAST) { set_error("call %u: bad column or function", i); delete q; return OG_E_INVAL; }
         int type = s->col_types[c.column];
+        if (type == OG_TYPE_STRING && c.func != OG_AGG_COUNT) { set_error("call %u: only count() is pushed down for string columns (their values are never decoded on the GPU path)", i); delete q; return OG_E_UNSUPPORTED; }
         if (c.func == OG_AGG_SUM && type == OG_TYPE_BOOL) { set_error("sum() over a boolean column (unsupported sum iterator type, series_call_processor.go:140)"); delete q; return OG_E_INVAL; }
         int sl = slot_of(c.column);
         if (sl < 0) { set_error("too many distinct columns"); delete q; return OG_E_INVAL; }
@@ -377,6 +378,7 @@ OG_API int og_query_create(og_shard *s, const og_query_desc *d_in, og_query **ou
         fp.kind = f.kind;
         if (f.kind == OG_F_TERM) {
             if (f.column < 0 || (uint32_t)f.column >= s->n_columns || f.op < OG_OP_LT || f.op > OG_OP_NEQ) { set_error("filter item %u: bad column or op", i); delete q; return OG_E_INVAL; }
+            if (s->col_types[f.column] == OG_TYPE_STRING) { set_error("filter item %u: WHERE on a string column is not pushed down", i); delete q; return OG_E_UNSUPPORTED; }
             int sl = slot_of(f.column);
             if (sl < 0) { set_error("too many distinct columns"); delete q; return OG_E_INVAL; }
             fp.col_slot = sl; fp.op = f.op; fp.type = s->col_types[f.column]; fp.const_is_float = f.const_is_float; fp.fval = f.fval; fp.ival = f.ival;
@@ -639,8 +641,11 @@ int build_plan(og_query *q) {
     pl->gp.grp_begin = d_grp_begin; pl->gp.grp_series = d_grp_series; pl->gp.n_groups = q->n_groups;
     for (uint32_t c = 0; c < p.n_calls; c++) pl->gp.dense[c] = q->dense[c];
 
-    pl->fused = p.n_cols == 1 && p.n_filter == 0 && !(q->desc.flags & OG_Q_NO_FUSED);
-    pl->multi = !pl->fused && p.n_cols <= OG_MULTI_MAXC && !(q->desc.flags & OG_Q_NO_FUSED);
+    bool has_string = false;
+    for (uint32_t k = 0; k < p.n_cols; k++) has_string |= p.col_type[k] == OG_TYPE_STRING;
+    if (has_string && p.n_cols > OG_MULTI_MAXC) { set_error("a query that counts a string column may touch at most %d columns", OG_MULTI_MAXC); return OG_E_UNSUPPORTED; }
+    pl->fused = p.n_cols == 1 && p.n_filter == 0 && !has_string && !(q->desc.flags & OG_Q_NO_FUSED);
+    pl->multi = !pl->fused && p.n_cols <= OG_MULTI_MAXC && (has_string || !(q->desc.flags & OG_Q_NO_FUSED));
     q->path_used = pl->fused ? 1 : pl->multi ? 4 : 0;
     const bool want_fast = pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments;
     if (want_fast && (rc = ensure_il(s, p.col_index[0], st))) return rc;
@@ -1071,7 +1076,32 @@ OG_API int og_decode_column_device(og_shard *s, uint32_t column, uint32_t seg_be
 }
 
 /* one segment -> Record view in pinned host memory (the KeyCursor.Next of a non-aggregating reader) */
-OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out) {
+/* descending scans hand every segment over reversed: values, validity bits and times (reader.go:516-519,1035-1042 reverseXxxValues) */
+__global__ void k_reverse_segment(uint8_t *vals, uint32_t elem_bytes, uint32_t n_vals, uint8_t *bitmap, uint32_t rows) {
+    for (uint32_t i = threadIdx.x; i < n_vals / 2; i += blockDim.x) {
+        const uint32_t j = n_vals - 1 - i;
+        if (elem_bytes == 8) { uint64_t *v = (uint64_t *)vals; const uint64_t a = v[i]; v[i] = v[j]; v[j] = a; }
+        else { const uint8_t a = vals[i]; vals[i] = vals[j]; vals[j] = a; }
+    }
+    if (!bitmap) return;
+    __syncthreads();
+    __shared__ uint8_t sbm[8192]; /* rows <= 65536 */
+    const uint32_t nb = (rows + 7) / 8;
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) sbm[i] = bitmap[i];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+        uint8_t o = 0;
+        for (uint32_t k = 0; k < 8 && i * 8 + k < rows; k++) { const uint32_t src = rows - 1 - (i * 8 + k); o |= (uint8_t)((sbm[src >> 3] >> (src & 7)) & 1) << k; }
+        bitmap[i] = o;
+    }
+}
+} // extern "C"
+static int decode_segment_impl(og_shard *s, uint32_t segment, uint32_t flags, og_record_view *out);
+extern "C" {
+OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out) { return decode_segment_impl(s, segment, 0, out); }
+OG_API int og_decode_segment_ex(og_shard *s, uint32_t segment, uint32_t flags, og_record_view *out) { return decode_segment_impl(s, segment, flags, out); }
+} // extern "C"
+static int decode_segment_impl(og_shard *s, uint32_t segment, uint32_t flags, og_record_view *out) {
     if (!s || !out || segment >= s->n_segments) { set_error("bad argument"); return OG_E_INVAL; }
     CU(cudaSetDevice(s->device));
     uint32_t R = std::max<uint32_t>(1, s->max_seg_rows);
@@ -1096,6 +1126,18 @@ OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out)
     int err[2]; cudaError_t e = cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost); dev_free(d_err);
     if (e != cudaSuccess) return cuda_fail(e, "k_decode_column", __FILE__, __LINE__);
     if (err[0]) { set_error("segment %d failed to decode (device code %d)", err[1], err[0]); return map_dev_err(err[0]); }
+    if (flags & OG_DECODE_DESCENDING) {
+        if (R > 65536) { set_error("descending materialisation supports segments of up to 65536 rows"); return OG_E_UNSUPPORTED; }
+        uint32_t hr[65]; /* non-null counts per column, rows in the last slot */
+        CU(cudaMemcpy(hr, drows, (ncol1) * 4, cudaMemcpyDeviceToHost));
+        const uint32_t rows_seg = hr[s->n_columns];
+        for (uint32_t c = 0; c <= s->n_columns; c++) {
+            const bool is_time = c == s->n_columns;
+            const uint32_t eb = (!is_time && s->col_types[c] == OG_TYPE_BOOL) ? 1 : 8;
+            k_reverse_segment<<<1, 256>>>(dv + c * val_stride, eb, is_time ? rows_seg : hr[c], is_time ? nullptr : dbm + c * bm_stride, rows_seg);
+        }
+        CU(cudaGetLastError());
+    }
     CU(cudaMemcpy(s->h_seg_buf, s->d_seg_buf, need, cudaMemcpyDeviceToHost));
     uint8_t *hv = (uint8_t *)s->h_seg_buf, *hbm = hv + ncol1 * val_stride;
     uint32_t *hrows = (uint32_t *)(hbm + ncol1 * bm_stride);
@@ -1113,5 +1155,3 @@ OG_API int og_decode_segment(og_shard *s, uint32_t segment, og_record_view *out)
     out->sid = s->sids[sr];
     return OG_OK;
 }
-
-} // extern "C"

@@ -25,7 +25,7 @@ namespace ogpu {
 
 /* next (valid, value) of one field column of one segment; value = raw 64-bit cell (double bits / int64 / bool 0,1) */
 struct ColIter {
-    enum { K_ABSENT = 0, K_ONE, K_F_RAW, K_F_GORILLA, K_F_SAME, K_F_RLE, K_I_CONST, K_I_S8B, K_I_RAW, K_B_BITS };
+    enum { K_ABSENT = 0, K_NULLMAP /* string column: validity only, values are never decoded */, K_ONE, K_F_RAW, K_F_GORILLA, K_F_SAME, K_F_RLE, K_I_CONST, K_I_S8B, K_I_RAW, K_B_BITS };
     PageHdr h;
     int kind, type;
     uint32_t row;      /* next row */
@@ -44,6 +44,7 @@ struct ColIter {
         if (rc != D_OK) { err = rc; kind = K_ABSENT; return; }
         const uint32_t n = h.rows - h.nil_count;
         if (n == 0) { kind = K_ABSENT; return; }
+        if (col_type == OG_TYPE_STRING) { kind = K_NULLMAP; return; } /* lib/encoding/string.go:286-302 is not needed for count(): ValidCount reads the bitmap */
         if (h.one_row) { kind = K_ONE; cur = col_type == OG_TYPE_BOOL ? (uint64_t)__ldg(h.block) : (h.block_len >= 8 ? ld_le64(h.block) : 0); if (col_type != OG_TYPE_BOOL && h.block_len < 8) err = D_CORRUPT; return; }
         if (h.block_len < 1) { err = D_CORRUPT; kind = K_ABSENT; return; }
         const uint8_t *in = h.block; const uint32_t bl = h.block_len - 1;

@@ -121,9 +121,9 @@ class Shard:
                 "og_shard_export")
         return out
 
-    def decode_segment(self, seg):
+    def decode_segment(self, seg, descending=False):
         rv = L.RecordView()
-        L.check(L.lib().og_decode_segment(self.h, seg, C.byref(rv)), "og_decode_segment")
+        L.check(L.lib().og_decode_segment_ex(self.h, seg, 1 if descending else 0, C.byref(rv)), "og_decode_segment_ex")
         return _record_to_py(rv)
 
     def close(self):
