@@ -569,7 +569,8 @@ def run_ours(a):
 def run_mixed(a):
     """configs[2] on one GPU: 50k series x 20k rows (10^9 rows) of int64 (Simple8b) + float64 (Gorilla, G-lo) + bool columns,
     count(i), sum(i), sum(f), count(b) WHERE f > 1000 GROUP BY time(1m); --nulls 50 = the 5 % nulls variant.  One step = one
-    og_query_run (k_fused_multi: every column a pull iterator, nothing materialised).  The answer is checked against the oracle
+    og_query_run (k_fused_cols: one thread per segment walks one column at a time in a codec-specialised loop, columns meet through
+    a per-thread row mask; nothing materialised.  OGPU_NO_COLS=1 selects the older pull-iterator kernel k_fused_multi).  The answer is checked against the oracle
     on a slice of the same synthetic population (series_base)."""
     import numpy as np
     import torch
@@ -619,9 +620,9 @@ def run_mixed(a):
                                    "count(i), sum(i), sum(f), count(b) WHERE f > 1000 GROUP BY time(1m), one tagset", "rows": int(info["n_rows"]),
                        "page_bytes": int(info["page_bytes"]), "compressed_bytes_per_row": info["page_bytes"] / max(1, info["n_rows"]),
                        "l2": "3 GB of pages per step: far larger than the 126 MB L2; no explicit flush"},
-            "clocks": clocks, "roofline": {"bound": "hbm", "kernel": "k_fused_multi<3>", "achieved": algo / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+            "clocks": clocks, "roofline": {"bound": "hbm", "kernel": "k_fused_cols" if st["path"] == 5 else "k_fused_multi", "achieved": algo / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                            "frac": algo / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
-                                           "kernel_ms": k_ms, "note": "instruction-bound: four codecs decoded per row by one thread; bytes per row are ~3"},
+                                           "kernel_ms": k_ms, "note": "instruction-bound: three codecs decoded per row by one thread; bytes per row are ~3"},
             "e2e": None, "cpu_baseline": None, "verify": verify, "gpu_launches": launches, "path": st["path"]}
     print(json.dumps(line), flush=True)
     q.close(); sh.close()

@@ -8,6 +8,9 @@
  *                            ChunkMeta.colMeta[i].entries[seg]{offset,size}, tssp_file_meta.go:60-63,377-385)
  *                            + lib/fileops/readcache page access.  Here: one upload of the data region + the
  *                            flattened ChunkMeta ("segment directory") into HBM.
+ *   og_tssp_parse/_desc      the directory half of the file open: footer -> trailer -> meta index -> chunk-meta blocks ->
+ *                            ChunkMeta (engine/immutable/trailer.go:71-88, tssp_file_meta.go:606-687,789-802,
+ *                            tssp_file.go:606-658); yields the og_shard_desc og_shard_open takes.  Host only.
  *   og_query_create/run      engine/iterators.go:130 shard.CreateCursor -> createGroupCursors :551 ->
  *                            NewAggregateCursor aggregate_cursor.go:65 + NewAggTagSetCursor agg_tagset_cursor.go:583;
  *                            SinkPlan (aggregate_cursor.go:208) builds what og_query_desc carries.
@@ -204,7 +207,8 @@ typedef struct og_stats {
     double main_kernel_ms;     /* of which: the dominant decode+reduce kernel(s) (k_fused_segment, or decode/filter/reduce tiles) */
     uint32_t kernel_launches;  /* kernels launched by the last og_query_run */
     int32_t path;              /* 0 generic materialise-tile path; 4 fused multi-column / WHERE kernel (pull iterators, nothing
-                                  materialised); 1 fused, general per-segment kernel only; 2 fused Gorilla kernel over the
+                                  materialised); 5 the column-at-a-time form of it (const-delta time pages, at most one WHERE
+                                  term: k_fused_cols); 1 fused, general per-segment kernel only; 2 fused Gorilla kernel over the
                                   lane-interleaved copy with per-series cells (strict order / tag groups / per-series output);
                                   3 the same with interior windows folded in-warp (one tagset, regular shard) */
     int32_t il_state;          /* lane-interleaved copy of the queried float column: 1 ready, 0 not applicable, -1 no eligible page,
@@ -228,6 +232,20 @@ OG_API const char *og_version(void);
 /* Device buffers of closed shards and destroyed queries stay in the device's memory pool for reuse (open/close loops do not pay
  * cudaMalloc/cudaFree); this hands the unused part back to the driver. */
 OG_API int og_release_cached_memory(void);
+
+/* ---- TSSP container -> shard description (host only; csrc/tssp.cpp).  Replaces the directory half of the reference's file
+ * open: footer -> Trailer.Unmarshal (engine/immutable/trailer.go:71-88, table_stat.go:51-84,144-207) -> MetaIndex.unmarshal
+ * (tssp_file_meta.go:789-802) -> chunk-meta blocks (tssp_file.go:606-658) -> ChunkMeta.unmarshal (tssp_file_meta.go:606-687,
+ * 248-303).  `file` must stay valid (and unchanged) until og_tssp_free; the description og_tssp_desc fills borrows from the
+ * handle and from `file` (page offsets are absolute file offsets, Segment.offset), and is what og_shard_open takes.  Series may
+ * have different columns: the description holds the union, sorted by name, page_len 0 where a chunk lacks the column.
+ * Compressed chunk metas (ChunkMetaCompressFlag != 0) and detached files are refused with OG_E_UNSUPPORTED. ---- */
+typedef struct og_tssp og_tssp;
+OG_API int og_tssp_parse(const uint8_t *file, uint64_t len, og_tssp **out);
+OG_API int og_tssp_desc(const og_tssp *t, og_shard_desc *out);
+OG_API const char *og_tssp_measurement(const og_tssp *t);                 /* TableStat.name */
+OG_API int og_tssp_time_range(const og_tssp *t, int64_t *min_time, int64_t *max_time); /* TableStat.minTime / maxTime */
+OG_API void og_tssp_free(og_tssp *t);
 
 /* ---- shard ---- */
 OG_API int og_shard_open(const og_shard_desc *desc, og_shard **out);

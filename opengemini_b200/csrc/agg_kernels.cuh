@@ -74,7 +74,7 @@ __device__ __forceinline__ void store_cell(const ChunkP &ch, int call, uint32_t 
 /* last time of a page and whether its times ascend (segments hold time-ordered rows, lib/record/record.go sort order) */
 struct LastTime { int64_t last; int unsorted = 0; __device__ __forceinline__ void operator()(uint32_t i, int64_t t) { if (i && t < last) unsorted = 1; last = t; } };
 
-__global__ void k_validate(DirP d, const int32_t *col_types, uint32_t *seg_rows, unsigned long long *totals /*[0]=rows [1]=page bytes*/,
+__global__ void k_validate(DirP d, const int32_t *col_types, uint32_t *seg_rows, unsigned long long *totals /*[0]=rows [1]=page bytes [2]=time pages that are not const-delta / one-row*/,
                            uint32_t *max_rows, int *err) {
     uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
     if (seg >= d.n_segments) return;
@@ -115,6 +115,7 @@ __global__ void k_validate(DirP d, const int32_t *col_types, uint32_t *seg_rows,
     atomicAdd(&totals[0], (unsigned long long)t.rows);
     atomicAdd(&totals[1], bytes);
     atomicMax(max_rows, t.rows);
+    if (t.kind != 0 && t.kind != 3) atomicAdd(&totals[2], 1ull);
 }
 
 __global__ void k_fill_seg_series(const uint32_t *series_seg_begin, uint32_t n_series, uint32_t *seg_series) {

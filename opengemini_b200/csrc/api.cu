@@ -12,6 +12,7 @@
 #include "fused.cuh"
 #include "il_build.cuh"
 #include "fused_multi.cuh"
+#include "fused_cols.cuh"
 #include "snappy_load.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -72,11 +73,11 @@ int shard_finalize(og_shard *s, bool scan_snappy) {
     if ((rc = dalloc(&s->d_seg_rows, s->n_segments))) return rc;
     int32_t *d_types; unsigned long long *d_tot; uint32_t *d_max; int *d_err;
     if ((rc = dalloc(&d_types, s->n_columns))) return rc;
-    if ((rc = dalloc(&d_tot, 2))) return rc;
+    if ((rc = dalloc(&d_tot, 3))) return rc;
     if ((rc = dalloc(&d_max, 1))) return rc;
     if ((rc = dalloc(&d_err, 2))) return rc;
     CU(cudaMemcpy(d_types, s->col_types.data(), s->n_columns * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU(cudaMemset(d_tot, 0, 16)); CU(cudaMemset(d_max, 0, 4)); CU(cudaMemset(d_err, 0, 8));
+    CU(cudaMemset(d_tot, 0, 24)); CU(cudaMemset(d_max, 0, 4)); CU(cudaMemset(d_err, 0, 8));
     if (s->n_series) k_fill_seg_series<<<s->n_series, 128>>>(s->d_series_seg_begin, s->n_series, s->d_seg_series);
     if (s->n_segments && scan_snappy) { /* Snappy pages -> raw pages appended behind the data (snappy_load.cuh) */
         const size_t n_pages = (size_t)(s->n_columns + 1) * s->n_segments;
@@ -111,8 +112,8 @@ int shard_finalize(og_shard *s, bool scan_snappy) {
     }
     if (s->n_segments) k_validate<<<(s->n_segments + 127) / 128, 128>>>(make_dir(s), d_types, s->d_seg_rows, d_tot, d_max, d_err);
     CU(cudaGetLastError());
-    unsigned long long tot[2]; int err[2]; uint32_t mx;
-    CU(cudaMemcpy(tot, d_tot, 16, cudaMemcpyDeviceToHost));
+    unsigned long long tot[3]; int err[2]; uint32_t mx;
+    CU(cudaMemcpy(tot, d_tot, 24, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(err, d_err, 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&mx, d_max, 4, cudaMemcpyDeviceToHost));
     dev_free(d_types); dev_free(d_tot); dev_free(d_max); dev_free(d_err);
@@ -121,7 +122,7 @@ int shard_finalize(og_shard *s, bool scan_snappy) {
         return map_dev_err(err[0]);
     }
     s->n_rows = tot[0]; s->page_bytes = tot[1] - s->snappy_bytes_out + s->snappy_bytes_in; /* algorithmic bytes = the pages as stored */
-    s->max_seg_rows = mx;
+    s->max_seg_rows = mx; s->irregular_time_pages = tot[2];
     return OG_OK;
 }
 
@@ -432,6 +433,7 @@ namespace {
 struct Plan { /* built once per query, reused by every og_query_run */
     ChunkP ch; TileP tp; GroupP gp;
     bool fused;
+    bool cols;      /* multi, served by the column-at-a-time kernel k_fused_cols */
     bool multi;     /* several columns and/or a WHERE: pull-iterator kernel k_fused_multi, nothing materialised */
     bool fast;      /* the fused Gorilla kernel serves the eligible segments, k_fused_segment the rest */
     bool blockmerge;/* one tagset, order not pinned, per-series cells: two-stage parallel merge (k_merge_all_blocks + k_merge_folded) */
@@ -491,6 +493,13 @@ template <int NCOL> void launch_multi_c(const QueryP &p, const DirP &d, const Ch
     case 7: return launch_multi_t<NCOL, 7>(p, d, ch, nseg, st);
     default: return launch_multi_t<NCOL, 8>(p, d, ch, nseg, st);
     }
+}
+void launch_cols(const QueryP &p, const DirP &d, const ChunkP &ch, uint32_t nseg, cudaStream_t st) {
+    bool simple = true;
+    for (uint32_t c = 0; c < p.n_calls; c++) simple &= p.calls[c].func == OG_AGG_COUNT || p.calls[c].func == OG_AGG_SUM;
+    const unsigned gb = (nseg + 127) / 128;
+    if (simple) k_fused_cols<true><<<gb, 128, 0, st>>>(d, p, ch);
+    else k_fused_cols<false><<<gb, 128, 0, st>>>(d, p, ch);
 }
 void launch_multi(const QueryP &p, const DirP &d, const ChunkP &ch, uint32_t nseg, cudaStream_t st) {
     switch (p.n_cols) {
@@ -643,10 +652,22 @@ int build_plan(og_query *q) {
 
     bool has_string = false;
     for (uint32_t k = 0; k < p.n_cols; k++) has_string |= p.col_type[k] == OG_TYPE_STRING;
-    if (has_string && p.n_cols > OG_MULTI_MAXC) { set_error("a query that counts a string column may touch at most %d columns", OG_MULTI_MAXC); return OG_E_UNSUPPORTED; }
     pl->fused = p.n_cols == 1 && p.n_filter == 0 && !has_string && !(q->desc.flags & OG_Q_NO_FUSED);
-    pl->multi = !pl->fused && p.n_cols <= OG_MULTI_MAXC && (has_string || !(q->desc.flags & OG_Q_NO_FUSED));
-    q->path_used = pl->fused ? 1 : pl->multi ? 4 : 0;
+    const bool multi_ok = !pl->fused && (has_string || !(q->desc.flags & OG_Q_NO_FUSED));
+    /* column-at-a-time kernel (fused_cols.cuh): const-delta time pages, <= one WHERE term, few calls per column; any number of columns */
+    pl->cols = false;
+    if (multi_ok && !(q->desc.flags & OG_Q_NO_FAST) && s->irregular_time_pages == 0 && s->max_seg_rows <= OG_COLS_MAXROWS &&
+        (p.n_filter == 0 || (p.n_filter == 1 && p.filter[0].kind == OG_F_TERM)) && !getenv("OGPU_NO_COLS")) {
+        pl->cols = true;
+        for (uint32_t k = 0; k < p.n_cols; k++) {
+            int n = 0;
+            for (uint32_t c = 0; c < p.n_calls; c++) n += p.calls[c].col_slot == (int)k;
+            if (n > OG_COLS_MAXMINE) pl->cols = false;
+        }
+    }
+    if (has_string && !pl->cols && p.n_cols > OG_MULTI_MAXC) { set_error("a query that counts a string column may touch at most %d columns on this shard", OG_MULTI_MAXC); return OG_E_UNSUPPORTED; }
+    pl->multi = pl->cols || (multi_ok && p.n_cols <= OG_MULTI_MAXC);
+    q->path_used = pl->fused ? 1 : pl->cols ? 5 : pl->multi ? 4 : 0;
     const bool want_fast = pl->fused && p.col_type[0] == OG_TYPE_FLOAT && !(q->desc.flags & OG_Q_NO_FAST) && s->n_segments;
     if (want_fast && (rc = ensure_il(s, p.col_index[0], st))) return rc;
     pl->fast = want_fast && s->il[p.col_index[0]].state == 1;
@@ -822,6 +843,8 @@ OG_API int og_query_run(og_query *q) {
                 }
                 launches++;
             }
+        } else if (pl->cols) {
+            launch_cols(p, dir, ch, nseg, st);
         } else if (pl->multi) {
             launch_multi(p, dir, ch, nseg, st);
             launches++;

@@ -42,6 +42,7 @@ struct og_shard {
     uint8_t *d_data = nullptr; uint64_t data_len = 0; bool owns_data = true;
     uint32_t n_series = 0, n_segments = 0, n_columns = 0;
     uint32_t max_seg_rows = 0;
+    uint64_t irregular_time_pages = 0; /* time pages that are neither const-delta nor one-row (Simple8b / raw times) */
     uint64_t n_rows = 0, page_bytes = 0;
     uint64_t snappy_pages = 0, snappy_bytes_in = 0, snappy_bytes_out = 0; /* Snappy pages transcoded to raw at open */
     int64_t tmin = 0, tmax = 0;
@@ -123,7 +124,7 @@ struct og_query {
     std::vector<std::vector<int64_t>> rv_coltimes;
     std::vector<int64_t> rv_times;
     std::vector<og_colval_view> rv_cols;
-    int path_used = 0; /* 0 generic tile path, 1 fused (general kernel), 2 fused Gorilla kernel, per-series cells, 3 fused Gorilla kernel, folded cells */
+    int path_used = 0; /* 0 generic tile path, 1 fused (general kernel), 2 fused Gorilla kernel, per-series cells, 3 fused Gorilla kernel, folded cells, 4 pull-iterator kernel k_fused_multi, 5 column-at-a-time kernel k_fused_cols */
     bool cells_dirty = true; /* per-series cell validity bytes need clearing before the next run */
     /* execution plan + scratch, built by the first og_query_run and reused by later runs */
     bool planned = false;

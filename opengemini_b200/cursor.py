@@ -92,6 +92,29 @@ class Shard:
         return cls(h.value, keepalive)
 
     @classmethod
+    def open_tssp(cls, file_bytes):
+        """Open a TSSP file image (bytes / numpy uint8): og_tssp_parse -> og_tssp_desc -> og_shard_open.  og_shard_open copies
+        what it needs, so the parse handle is freed before returning; `measurement` and `time_range` are kept on the Shard."""
+        import numpy as np
+        buf = np.frombuffer(file_bytes, dtype=np.uint8) if not isinstance(file_bytes, np.ndarray) else np.ascontiguousarray(file_bytes, dtype=np.uint8)
+        t = C.c_void_p()
+        L.check(L.lib().og_tssp_parse(buf.ctypes.data, buf.size, C.byref(t)), "og_tssp_parse")
+        try:
+            d = L.ShardDesc()
+            L.check(L.lib().og_tssp_desc(t, C.byref(d)), "og_tssp_desc")
+            lo, hi = C.c_int64(), C.c_int64()
+            L.check(L.lib().og_tssp_time_range(t, C.byref(lo), C.byref(hi)), "og_tssp_time_range")
+            name = L.lib().og_tssp_measurement(t)
+            columns = [(d.columns[c].name.decode(), int(d.columns[c].type)) for c in range(d.n_columns)]
+            h = C.c_void_p()
+            L.check(L.lib().og_shard_open(C.byref(d), C.byref(h)), "og_shard_open")
+        finally:
+            L.lib().og_tssp_free(t)
+        sh = cls(h.value)
+        sh.measurement, sh.time_range, sh.columns = name.decode(), (lo.value, hi.value), columns
+        return sh
+
+    @classmethod
     def synth(cls, n_series, rows_per_series, columns, t0=1_700_000_000_000_000_000, dt=1_000_000_000, seed=1,
               rows_per_segment=1000, series_base=0):
         """columns: list of (type, dist, null_permille). Builds the shard on the device with the encode kernels."""

@@ -597,3 +597,45 @@ def test_two_stage_merge_of_per_series_cells(monkeypatch):
         compare_dense(q.dense_host(), ref, calls, len(calls) > 1, f"blockmerge {calls}", float_sum_exact=False)
         q.close()
     sh.close()
+
+
+def test_column_at_a_time_kernel_and_pull_iterator_kernel_agree_with_the_oracle(agg_shard, monkeypatch):
+    """Queries over several columns / one WHERE term run k_fused_cols (path 5) on const-delta shards; OGPU_NO_COLS selects the
+    older k_fused_multi (path 4).  Both must equal the oracle bitwise (run_both) on: columns with and without nulls, every
+    call kind, ranges that cut segments, windows shorter than the cadence, one window for everything."""
+    sh, hs = agg_shard
+    tmax = T0 + 4320 * SEC
+    cases = [
+        ([("sum", 0), ("count", 4), ("max", 3), ("last", 5), ("min", 1)], None, 60 * SEC, T0, tmax, {}),
+        ([("count", 1), ("sum", 1), ("sum", 3), ("count", 5)], [("term", 3, ">", 1000.0)], 60 * SEC, T0, tmax, {}),
+        ([("count", 1), ("sum", 0), ("count", 2), ("sum", 4)], [("term", 4, "<", 0)], 7 * SEC, T0 + 1234 * SEC + 5, T0 + 3456 * SEC + 7, {}),
+        ([("first", 0), ("last", 0), ("min", 3), ("max", 3)], [("term", 2, "=", 1)], 3600 * SEC, T0 - 500 * SEC, T0 + 10_000 * SEC, dict(offset=7 * SEC)),
+        ([("sum", 3), ("count", 3), ("sum", 4), ("count", 4), ("count", 5)], None, 0, T0 + 999 * SEC, T0 + 1001 * SEC, {}),
+        ([("max", 4)], [("term", 0, ">", 100.5)], 61 * SEC, T0 + 17, T0 + 4000 * SEC, dict(offset=-13 * SEC, group="series")),
+        ([("sum", 1), ("sum", 0)], [("term", 5, "!=", 1)], 300 * SEC, T0, tmax, dict(group="map", series_group=[2, 0, 1, 0, 2, 2, 0], n_groups=3)),
+    ]
+    for no_cols, want in (("", 5), ("1", 4)):
+        if no_cols:
+            monkeypatch.setenv("OGPU_NO_COLS", no_cols)
+        for calls, flt, iv, t0, t1, kw in cases:
+            q = AggQuery(sh, calls, iv, t0, t1, filter=flt, **kw).run()
+            ncols = len({c for _, c in calls} | {t[1] for t in (flt or []) if isinstance(t, tuple)})
+            assert q.stats()["path"] == (want if want == 5 or ncols <= 4 else 0), (calls, flt)  # the pull-iterator kernel takes <= 4 columns
+            q.close()
+            run_both(sh, hs.desc, calls, iv, t0, t1, f"cols={want} {calls} where {flt}", filter=flt, **kw)
+    monkeypatch.delenv("OGPU_NO_COLS")
+    # cadence longer than the window (windows without rows), and all rows on one timestamp is not a const-delta page the encoder
+    # produces; long segments (> 1024 rows) fall back to the pull-iterator kernel
+    cols = [(L.TYPE_FLOAT, L.SYNTH_F_LO, 0), (L.TYPE_INT, L.SYNTH_INT_WALK, 300), (L.TYPE_BOOL, L.SYNTH_BOOL, 0)]
+    hs2 = oracle.HostShard(5, 2345, cols, t0=T0, dt=90 * SEC, seed=77)
+    sh2 = Shard.open_desc(hs2.desc, keepalive=hs2)
+    for flt in (None, [("term", 0, ">", 1000.0)]):
+        run_both(sh2, hs2.desc, [("sum", 0), ("count", 1), ("count", 2), ("sum", 1)], 60 * SEC, T0 + 100 * SEC, T0 + 2000 * 90 * SEC, f"sparse windows where {flt}", filter=flt)
+    sh2.close()
+    hs3 = oracle.HostShard(3, 5000, cols, t0=T0, dt=SEC, seed=78, rows_per_segment=2000)
+    sh3 = Shard.open_desc(hs3.desc, keepalive=hs3)
+    q = AggQuery(sh3, [("sum", 0), ("count", 1)], 60 * SEC, T0, T0 + 4999 * SEC).run()
+    assert q.stats()["path"] == 4
+    q.close()
+    run_both(sh3, hs3.desc, [("sum", 0), ("count", 1)], 60 * SEC, T0, T0 + 4999 * SEC, "2000-row segments")
+    sh3.close()
