@@ -33,26 +33,22 @@ namespace ogpu {
 #define OG_COLS_MAXROWS 1024u
 #define OG_COLS_MAXMINE 4
 
-/* 64 bits of a big-endian bit stream at any bit position, from three cached 32-bit words */
+/* 64 bits of a big-endian bit stream at any bit position, from cached 32-bit words: wa, wb, wc hold words wi, wi+1, wi+2 (what a
+ * 64-bit read at a bit offset inside word wi needs), wd holds word wi+3 — loaded one refill before it is first used, so the load
+ * latency overlaps a few records of decoding instead of stalling the read that follows */
 struct BitWin {
-    const uint32_t *base; uint32_t wa, wb, wc, wi;
+    const uint32_t *base; uint32_t wa, wb, wc, wd, wi;
     __device__ __forceinline__ uint32_t ldw(uint32_t i) const { return __byte_perm(__ldg(base + i), 0, 0x0123); }
     /* returns the bit offset of `p` inside the aligned word stream */
     __device__ __forceinline__ uint32_t init(const uint8_t *p) {
         const uintptr_t a = (uintptr_t)p;
         base = (const uint32_t *)(a & ~(uintptr_t)3);
-        wi = 0; wa = ldw(0); wb = ldw(1); wc = ldw(2);
+        wi = 0; wa = ldw(0); wb = ldw(1); wc = ldw(2); wd = ldw(3);
         return (uint32_t)(a & 3) * 8;
     }
     __device__ __forceinline__ uint64_t peek(uint32_t P) {
         const uint32_t word = P >> 5;
-        if (word != wi) {
-            const uint32_t d = word - wi;
-            if (d == 1) { wa = wb; wb = wc; wc = ldw(word + 2); }
-            else if (d == 2) { wa = wc; wb = ldw(word + 1); wc = ldw(word + 2); }
-            else { wa = ldw(word); wb = ldw(word + 1); wc = ldw(word + 2); }
-            wi = word;
-        }
+        while (wi != word) { wa = wb; wb = wc; wc = wd; wi++; wd = ldw(wi + 3); } /* a record moves the position by <= 77 bits: <= 3 steps */
         const uint32_t sh = P & 31;
         return ((uint64_t)__funnelshift_l(wb, wa, sh) << 32) | __funnelshift_l(wc, wb, sh);
     }
@@ -82,8 +78,9 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
                                           int nm, const int (&mc)[OG_COLS_MAXMINE]) {
     /* ---- decoder state in registers ---- */
     BitWin bw; uint32_t P = 0, gend = 0, tr = 0, mb = 64; uint64_t cur = it.cur;       /* Gorilla */
-    uint64_t sw = 0, smask = 0; uint32_t sbits = 0, sleft = 0, swords = it.words_left;  /* Simple8b */
+    uint64_t sw = 0, smask = 0, snext = 0; uint32_t sbits = 0, sleft = 0, swords = it.words_left;  /* Simple8b */
     const uint8_t *sp = it.p;
+    if (KIND == CK_S8B && swords) snext = ld_be64(sp); /* the next word is always loaded one refill ahead of its use */
     uint32_t bbyte = 0;                                                                  /* bool */
     uint32_t idx = 0;                                                                    /* values consumed */
     if (KIND == CK_GORILLA) { const uint32_t b0 = bw.init(it.p); P = b0; gend = b0 + it.c; }
@@ -113,7 +110,8 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
             if (i == 0) return cur;
             while (sleft == 0) {
                 if (swords == 0) { it.err = D_CORRUPT; return cur; }
-                sw = ld_be64(sp); sp += 8; swords--;
+                sw = snext; sp += 8; swords--;
+                if (swords) snext = ld_be64(sp);
                 unsigned nn; s8b_sel_packed((unsigned)(sw >> 60), nn, sbits);
                 sleft = nn;
                 if (sbits == 0) { sw = ~0ull; smask = 1; } /* selectors 0/1: runs of the value 1 */
@@ -140,7 +138,23 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
         if ((b >> 3) != vb_i) { vb_i = b >> 3; vb = __ldg(bm + vb_i); }
         return (vb >> (b & 7)) & 1;
     };
+    /* the WHERE term as four outcome masks (functions.go:632 semantics as term_pass states them: ordered tests pass NaN,
+     * = fails it): pass = lt&m_lt | gt&m_gt | eq&m_eq | unordered&m_un */
     const FilterP &f = q.filter[0];
+    const bool f_dbl = f.type == OG_TYPE_FLOAT || (f.type == OG_TYPE_INT && f.const_is_float);
+    const double f_cd = f.const_is_float ? f.fval : (double)f.ival;
+    const int64_t f_ci = f.ival;
+    const bool m_lt = f.op == OG_OP_LT || f.op == OG_OP_LTE || f.op == OG_OP_NEQ, m_gt = f.op == OG_OP_GT || f.op == OG_OP_GTE || f.op == OG_OP_NEQ;
+    const bool m_eq = f.op == OG_OP_LTE || f.op == OG_OP_GTE || f.op == OG_OP_EQ, m_un = f.op != OG_OP_EQ;
+    auto term = [&](uint64_t raw) -> bool {
+        if (f_dbl) {
+            const double v = f.type == OG_TYPE_FLOAT ? u2d(raw) : (double)(int64_t)raw;
+            const bool lt = v < f_cd, gt = v > f_cd, eq = v == f_cd;
+            return (lt && m_lt) || (gt && m_gt) || (eq && m_eq) || (!(lt || gt || eq) && m_un);
+        }
+        const int64_t v = f.type == OG_TYPE_BOOL ? (int64_t)(raw != 0) : (int64_t)raw;
+        return (v < f_ci && m_lt) || (v > f_ci && m_gt) || (v == f_ci && m_eq);
+    };
     int op[OG_COLS_MAXMINE]; /* SIMPLE: 0 count, 1 float sum, 2 integer sum */
 #pragma unroll
     for (int j = 0; j < OG_COLS_MAXMINE; j++) {
@@ -155,34 +169,44 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
     /* ---- windows ---- */
     Part parts[OG_COLS_MAXMINE];
     uint32_t cur_b = sg.b_first, rb = sg.rb_first, w = 0; uint64_t rem = sg.rem_first;
-    uint32_t kw = (MODE == 2) ? keep[r >> 5] : 0u;
+    uint32_t kw = (MODE == 2) ? keep[r >> 5] >> (r & 31) : 0u; /* MODE 2: bit 0 = the keep bit of row r */
+    /* SIMPLE (count / sum only): whatever the calls on this column are, they are functions of the count of taken rows and of one
+     * running sum — two accumulators per pass instead of one per call */
+    const bool fcol = it.type == OG_TYPE_FLOAT;
+    uint64_t cnt = 0, isum = 0; double fsum = 0.0;
     while (r <= sg.r_hi) {
         const uint32_t stop = rb < sg.r_hi + 1 ? rb : sg.r_hi + 1;
+        if (SIMPLE) { cnt = 0; isum = 0; fsum = 0.0; }
+        else {
 #pragma unroll
-        for (int j = 0; j < OG_COLS_MAXMINE; j++) parts[j] = part_empty();
+            for (int j = 0; j < OG_COLS_MAXMINE; j++) parts[j] = part_empty();
+        }
         for (; r < stop; r++) {
             const bool ok = valid(r);
             uint64_t v = 0;
             if (ok) v = next_value();
             bool kp = true;
             if (MODE == 1) {
-                kp = ok && term_pass(f, v);
+                kp = ok && term(v);
                 kw |= (uint32_t)kp << (r & 31);
                 if ((r & 31) == 31) { keep[r >> 5] = kw; kw = 0; }
             } else if (MODE == 2) {
                 if ((r & 31) == 0) kw = keep[r >> 5];
-                kp = (kw >> (r & 31)) & 1;
+                kp = kw & 1; kw >>= 1;
             }
-            if (kp && ok) {
+            const bool take = kp && ok;
+            if (SIMPLE) { /* count: += 1; sum: sequential add in row order (integerSumReduce / floatSumReduce).  No branch on `take`:
+                           * lanes disagree on it row by row.  Adding +0.0 leaves a float sum unchanged bit for bit (a sum that
+                           * starts at +0.0 is never -0.0) */
+                cnt += (uint64_t)take;
+                if (fcol) fsum += take ? u2d(v) : 0.0;
+                else isum += take ? v : 0ull;
+            } else if (take) {
 #pragma unroll
                 for (int j = 0; j < OG_COLS_MAXMINE; j++) {
                     if (j >= nm) break;
-                    if (SIMPLE) { /* count: += 1; sum: sequential add in row order (integerSumReduce / floatSumReduce) */
-                        if (op[j] == 0) parts[j].v += 1;
-                        else if (op[j] == 1) parts[j].v = d2u(u2d(parts[j].v) + u2d(v));
-                        else parts[j].v += v;
-                        parts[j].ok = 1;
-                    } else { const CallP &cp = q.calls[mc[j]]; acc_row(cp.func, cp.type, parts[j], v, sg.t0 + (int64_t)r * sg.dt); }
+                    const CallP &cp = q.calls[mc[j]];
+                    acc_row(cp.func, cp.type, parts[j], v, sg.t0 + (int64_t)r * sg.dt);
                 }
             }
         }
@@ -190,6 +214,7 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
 #pragma unroll
         for (int j = 0; j < OG_COLS_MAXMINE; j++) {
             if (j >= nm) break;
+            if (SIMPLE) { parts[j].t = 0; parts[j].ok = cnt != 0; parts[j].v = op[j] == 0 ? cnt : op[j] == 1 ? d2u(fsum) : isum; }
             if (w == 0) store_part(ch.edges[mc[j]], sg.e, parts[j]);
             else if (final) store_part(ch.edges[mc[j]], sg.e + 1, parts[j]);
             else if (parts[j].ok) store_cell(ch, mc[j], sg.series, cur_b, parts[j]);
@@ -229,8 +254,11 @@ __device__ __forceinline__ void cols_column(const DirP &d, const QueryP &q, cons
     if (it.err != D_OK) report_err(ch.err, it.err, sg.seg);
 }
 
+#ifndef OG_COLS_MINB
+#define OG_COLS_MINB 10 /* blocks/SM the register cap allows; measured at configs[2]: 4 -> 52, 5 -> 62, 6 -> 64, 8 -> 71, 10 -> 73, 12 -> 74 G rows/s */
+#endif
 template <bool SIMPLE>
-__global__ void __launch_bounds__(128) k_fused_cols(DirP d, QueryP q, ChunkP ch) {
+__global__ void __launch_bounds__(128, SIMPLE ? OG_COLS_MINB : 4) k_fused_cols(DirP d, QueryP q, ChunkP ch) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     ColsSeg sg;
     sg.seg = ch.seg_begin + i;
