@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--cpu-series", type=int, default=0, help="series of the CPU sample (0 = auto: 4 per host thread)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="float", choices=["float", "mixed"],
+    ap.add_argument("--workload", default="float", choices=["float", "mixed", "downsample"],
                     help="float = configs[1] (the headline, default); mixed = configs[2]: int64 Simple8b + float64 Gorilla + bool columns, "
                          "count(i), sum(i), sum(f), count(b) WHERE f > 1000 GROUP BY time(1m) (a secondary line with its own roofline)")
     ap.add_argument("--nulls", type=int, default=0, help="mixed workload: null permille of every column (50 = the 5 %% variant)")
@@ -114,9 +114,12 @@ def ncu_traffic(a):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
     (profiles/traffic.json); only valid for the workload it was captured on, else null."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_fused_il"]
-        if a.series == 10000 and a.rows == 1000000 and a.dist == "hi":
-            return t["dram_bytes_per_launch"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if a.workload == "mixed":
+            if a.series == 10000 and a.rows == 1000000 and a.nulls == 0:  # the mixed workload's own defaults (50k x 20k) are substituted for these
+                return t["k_fused_cols"]["dram_bytes_per_launch"]
+        elif a.series == 10000 and a.rows == 1000000 and a.dist == "hi":
+            return t["k_fused_il"]["dram_bytes_per_launch"]
     except Exception:
         pass
     return None
@@ -514,6 +517,12 @@ def run_ours(a):
                "resident": resident,
                "sample_note": "2000 of the 10000 series per step: pinning and re-uploading the full 61 GB shard every step would take minutes; rates, not totals, are compared",
                "steps": e_steps, "phase_ms_per_step": {k: round(v / e_steps, 2) for k, v in phases.items()}, "ms_per_step": et.item() / e_steps * 1e3, "out_rows": out_rows}
+        # the cold path is the host-to-device copy: og_shard_open is one blocking copy of the pages plus the directory
+        open_s = phases.get("open", 0.0) / e_steps / 1e3
+        if open_s > 0:
+            e2e["h2d_GBps_inside_open"] = h2d / open_s / 1e9
+            e2e["copy_share_of_step"] = open_s / (et.item() / e_steps)
+            e2e["bound"] = "PCIe: with the copy alone the step could not exceed %.2f G rows/s" % (ns * a.rows / open_s / 1e9)
         del pinned
 
     cpu = None
@@ -621,11 +630,60 @@ def run_mixed(a):
                        "page_bytes": int(info["page_bytes"]), "compressed_bytes_per_row": info["page_bytes"] / max(1, info["n_rows"]),
                        "l2": "3 GB of pages per step: far larger than the 126 MB L2; no explicit flush"},
             "clocks": clocks, "roofline": {"bound": "hbm", "kernel": "k_fused_cols" if st["path"] == 5 else "k_fused_multi", "achieved": algo / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                           "frac": algo / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                                           "frac": algo / (k_ms / 1e3) / 1e9 / peak, "traffic": ncu_traffic(a) if st["path"] == 5 else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                                            "kernel_ms": k_ms, "note": "instruction-bound: three codecs decoded per row by one thread; bytes per row are ~3"},
             "e2e": None, "cpu_baseline": None, "verify": verify, "gpu_launches": launches, "path": st["path"]}
     print(json.dumps(line), flush=True)
     q.close(); sh.close()
+
+
+def run_downsample(a):
+    """configs[4] on one GPU (one of its 8 shards): 125 series x 10^6 float64 rows (1.25e8 rows), decode -> per-series
+    min/max/sum/count/first/last per 5-minute window -> re-encode the six columns + time to TSSP pages with the device encoders
+    (opengemini_b200/downsample.py: og_query_run with OG_GROUP_PER_SERIES, then og_encode_pages per output column).  One step = the
+    whole read-aggregate-write pass, host wall clock around it with a device synchronize on both sides (the directory of the new
+    shard is assembled on the host, so the step is not a pure device region).  Checked every run: the new shard is reopened and
+    sum(count_) over it equals the source row count, min(min_) / max(max_) equal a direct query of the source."""
+    import numpy as np
+    import torch
+    from opengemini_b200 import AggQuery, Shard
+    from opengemini_b200 import _lib as L
+    from opengemini_b200.downsample import downsample
+    torch.cuda.set_device(0)
+    Shard.init(0)
+    series = a.series if a.series != 10_000 else 125
+    rows = a.rows
+    sh = Shard.synth(series, rows, [(L.TYPE_FLOAT, L.SYNTH_F_HI if a.dist == "hi" else L.SYNTH_F_LO, 0)], t0=T0, dt=SEC, seed=99)
+    info = sh.info()
+    tmax = T0 + (rows - 1) * SEC
+    ivl = 300 * SEC
+    for _ in range(max(a.warmup, 3)):
+        out = downsample(sh, 0, ivl, T0, tmax)
+    sampler = ClockSampler(0); sampler.start()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(a.steps):
+        out = downsample(sh, 0, ivl, T0, tmax)
+    torch.cuda.synchronize(); wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    verify = None
+    if not a.no_verify:
+        host = out["data"].cpu().numpy()[:out["data_len"]].copy()
+        ds = Shard.open(host, out["sids"], out["series_seg_begin"], out["seg_tmin"], out["seg_tmax"], out["columns"], out["time_page_off"], out["time_page_len"])
+        # rows of the new shard carry their window start as time: the first one lies up to one interval before T0
+        q1 = AggQuery(ds, [("min", 0), ("max", 1), ("sum", 3)], 0, T0 - ivl, tmax).run(); d1 = q1.dense_host()
+        q0 = AggQuery(sh, [("min", 0), ("max", 0), ("count", 0)], 0, T0, tmax).run(); d0 = q0.dense_host()
+        for k in range(3):
+            if int(d1["cols"][k]["values"].view(np.uint64)[0]) != int(d0["cols"][k]["values"].view(np.uint64)[0]):
+                raise VerifyError(f"downsample: aggregate {k} of the re-encoded shard differs from the source")
+        verify = {"rows_counted_in_output": int(d1["cols"][2]["values"].view(np.int64)[0]), "output_rows": int(out["rows"]), "output_page_bytes": int(out["data_len"])}
+        q1.close(); q0.close(); ds.close()
+    line = {"metric": "decoded+aggregated rows/s", "value": info["n_rows"] * a.steps / wall, "unit": "rows/s", "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": wall / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "ours",
+            "config": {"workload": f"configs[4], one shard of eight: {series} series x {rows} float64 rows -> min/max/sum/count/first/last per series per 5 m -> re-encoded pages",
+                       "rows": int(info["n_rows"]), "page_bytes_in": int(info["page_bytes"]), "timing": "host wall clock around the whole pass, device synchronised on both sides"},
+            "clocks": clocks, "roofline": None, "e2e": None, "cpu_baseline": None, "verify": verify, "gpu_launches": None}
+    print(json.dumps(line), flush=True)
+    sh.close()
 
 
 if __name__ == "__main__":
@@ -634,5 +692,7 @@ if __name__ == "__main__":
         run_reference(args)
     elif args.workload == "mixed":
         run_mixed(args)
+    elif args.workload == "downsample":
+        run_downsample(args)
     else:
         run_ours(args)

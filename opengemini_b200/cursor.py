@@ -181,6 +181,55 @@ def _record_to_py(rv):
     return dict(cols=cols, times=times, rows=rv.rows, group=rv.group, sid=rv.sid)
 
 
+class ScanCursor:
+    """Record materialisation for non-aggregating callers: the KeyCursor.Next() of a plain scan (what HybridStoreReader drains,
+    engine/hybrid_store_reader.go:444; per file it is Location.readData, engine/immutable/location.go:261-330: segments of a
+    chunk in time order — reversed for descending scans — pruned by ChunkMeta.timeRange, decoded by decodeColumnData
+    reader.go:674 and cut to the query range by FilterByTime reader.go:754).
+
+    One record per qualifying segment: series in shard order, a series' segments oldest first (latest first when
+    ascending=False, with the rows of each record reversed by the device: og_decode_segment_ex OG_DECODE_DESCENDING).  Rows
+    outside [tmin, tmax] are dropped; a column's `values` stay dense over its non-null rows, like ColVal.Val."""
+
+    def __init__(self, shard, tmin, tmax, ascending=True):
+        self.shard, self.tmin, self.tmax, self.ascending = shard, tmin, tmax, ascending
+        lay = L.ShardLayout()
+        L.check(L.lib().og_shard_layout_get(shard.h, C.byref(lay)), "og_shard_layout_get")
+        ns, ng = lay.n_series, lay.n_segments
+        self.sids, self.ssb = np.empty(ns, np.uint64), np.empty(ns + 1, np.uint32)
+        self.seg_tmin, self.seg_tmax = np.empty(ng, np.int64), np.empty(ng, np.int64)
+        L.check(L.lib().og_shard_export(shard.h, None, self.sids.ctypes.data, self.ssb.ctypes.data, self.seg_tmin.ctypes.data,
+                                        self.seg_tmax.ctypes.data, None, None, None), "og_shard_export")
+
+    def segments(self):
+        """(series index, segment) in emission order, after time-range pruning (location.go:276-280)."""
+        for s in range(self.sids.size):
+            segs = range(int(self.ssb[s]), int(self.ssb[s + 1]))
+            for g in (segs if self.ascending else reversed(segs)):
+                if self.seg_tmax[g] >= self.tmin and self.seg_tmin[g] <= self.tmax:
+                    yield s, g
+
+    def __iter__(self):
+        for s, g in self.segments():
+            rec = self.shard.decode_segment(g, descending=not self.ascending)
+            t = rec["times"]
+            keep = (t >= self.tmin) & (t <= self.tmax)
+            if not keep.all():
+                if not keep.any():
+                    continue
+                for c in rec["cols"]:
+                    dense_keep = keep[c["valid"]]  # the kept rows among the non-null ones
+                    c["values"] = c["values"][dense_keep]
+                    c["valid"] = c["valid"][keep]
+                    c["len"] = int(keep.sum())
+                    c["nil_count"] = int(c["len"] - c["valid"].sum())
+                rec["times"] = t[keep]
+                rec["rows"] = int(keep.sum())
+            rec["sid"] = int(self.sids[s])
+            rec["segment"] = g
+            yield rec
+
+
 class AggQuery:
     """calls: list of (func_name, column); filter: RPN list of ("term", column, op, const) | "and" | "or"."""
 
