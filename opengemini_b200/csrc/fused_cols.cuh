@@ -27,6 +27,7 @@
 #pragma once
 #include "fused_multi.cuh"
 #include "fused_il.cuh"
+#include <type_traits>
 
 namespace ogpu {
 
@@ -138,22 +139,26 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
         if ((b >> 3) != vb_i) { vb_i = b >> 3; vb = __ldg(bm + vb_i); }
         return (vb >> (b & 7)) & 1;
     };
-    /* the WHERE term as four outcome masks (functions.go:632 semantics as term_pass states them: ordered tests pass NaN,
-     * = fails it): pass = lt&m_lt | gt&m_gt | eq&m_eq | unordered&m_un */
+    /* the WHERE term (functions.go:632 semantics as term_pass states them: ordered tests pass NaN, = fails it) as an outcome
+     * table indexed by (v < c) + 2 (v > c) + 4 (v == c); index 0 = unordered */
     const FilterP &f = q.filter[0];
-    const bool f_dbl = f.type == OG_TYPE_FLOAT || (f.type == OG_TYPE_INT && f.const_is_float);
+    const int f_mode = f.type == OG_TYPE_FLOAT ? 0 : (f.type == OG_TYPE_INT && f.const_is_float) ? 1 : f.type == OG_TYPE_BOOL ? 3 : 2;
     const double f_cd = f.const_is_float ? f.fval : (double)f.ival;
     const int64_t f_ci = f.ival;
-    const bool m_lt = f.op == OG_OP_LT || f.op == OG_OP_LTE || f.op == OG_OP_NEQ, m_gt = f.op == OG_OP_GT || f.op == OG_OP_GTE || f.op == OG_OP_NEQ;
-    const bool m_eq = f.op == OG_OP_LTE || f.op == OG_OP_GTE || f.op == OG_OP_EQ, m_un = f.op != OG_OP_EQ;
+    const uint32_t f_lt = f.op == OG_OP_LT || f.op == OG_OP_LTE || f.op == OG_OP_NEQ, f_gt = f.op == OG_OP_GT || f.op == OG_OP_GTE || f.op == OG_OP_NEQ;
+    const uint32_t f_eq = f.op == OG_OP_LTE || f.op == OG_OP_GTE || f.op == OG_OP_EQ, f_un = f.op != OG_OP_EQ;
+    const uint32_t f_tab = f_un | (f_lt << 1) | (f_gt << 2) | (f_eq << 4);
     auto term = [&](uint64_t raw) -> bool {
-        if (f_dbl) {
-            const double v = f.type == OG_TYPE_FLOAT ? u2d(raw) : (double)(int64_t)raw;
-            const bool lt = v < f_cd, gt = v > f_cd, eq = v == f_cd;
-            return (lt && m_lt) || (gt && m_gt) || (eq && m_eq) || (!(lt || gt || eq) && m_un);
+        uint32_t idx;
+        if (f_mode <= 1) {
+            double v;
+            if (f_mode == 0) v = u2d(raw); else v = (double)(int64_t)raw;
+            idx = (uint32_t)(v < f_cd) + 2u * (uint32_t)(v > f_cd) + 4u * (uint32_t)(v == f_cd);
+        } else {
+            const int64_t v = f_mode == 3 ? (int64_t)(raw != 0) : (int64_t)raw;
+            idx = (uint32_t)(v < f_ci) + 2u * (uint32_t)(v > f_ci) + 4u * (uint32_t)(v == f_ci);
         }
-        const int64_t v = f.type == OG_TYPE_BOOL ? (int64_t)(raw != 0) : (int64_t)raw;
-        return (v < f_ci && m_lt) || (v > f_ci && m_gt) || (v == f_ci && m_eq);
+        return (f_tab >> idx) & 1;
     };
     int op[OG_COLS_MAXMINE]; /* SIMPLE: 0 count, 1 float sum, 2 integer sum */
 #pragma unroll
@@ -162,9 +167,12 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
         op[j] = cp.func == OG_AGG_COUNT ? 0 : cp.type == OG_TYPE_FLOAT ? 1 : 2;
     }
 
+    /* the row loops exist twice: NOBM = Full page (every row valid: no validity test per row), else bitmap / all-null */
+    auto run = [&](auto nobm_tag) {
+    constexpr bool NOBM = decltype(nobm_tag)::value;
     /* ---- rows before the query range only advance the decoder ---- */
     uint32_t r = 0;
-    for (; r < sg.r_lo; r++) if (valid(r)) (void)next_value();
+    for (; r < sg.r_lo; r++) if (NOBM || valid(r)) (void)next_value();
 
     /* ---- windows ---- */
     Part parts[OG_COLS_MAXMINE];
@@ -182,7 +190,7 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
             for (int j = 0; j < OG_COLS_MAXMINE; j++) parts[j] = part_empty();
         }
         for (; r < stop; r++) {
-            const bool ok = valid(r);
+            const bool ok = NOBM || valid(r);
             uint64_t v = 0;
             if (ok) v = next_value();
             bool kp = true;
@@ -228,6 +236,8 @@ __device__ __forceinline__ void cols_pass(const QueryP &q, const ChunkP &ch, con
         }
     }
     if (MODE == 1 && (sg.r_hi & 31) != 31) keep[sg.r_hi >> 5] = kw;
+    };
+    if (!bm && all_ok) run(std::true_type{}); else run(std::false_type{});
 }
 
 template <int MODE, bool SIMPLE>
