@@ -27,6 +27,8 @@
  *                            HybridStoreReader-style callers, engine/hybrid_store_reader.go:444).
  *   og_encode_pages          engine/immutable/column_builder.go:151-349 enc*Column + EncodeColumnHeader :428,
  *                            chunkdata_builder.go:65 EncodeTime (downsample / compaction re-encode).
+ *   og_downsample            engine/record_plan.go:494-830 + engine/immutable/stream_downsample.go:454-600: one column of a shard
+ *                            -> per-series window aggregates -> re-encoded pages and their directory, in one call.
  *   og_shard_synth           test/bench tooling: builds a synthetic shard directly in HBM with the encode kernels
  *                            (same bytes the oracle's restated encoders produce; see tests/test_gpu_parity.py::test_synth_pages_byte_exact).
  *
@@ -333,6 +335,20 @@ OG_API int og_encode_pages(int32_t type, int32_t is_time, const void *d_values, 
                            const uint32_t *d_rows /*[n_segments] rows in each segment*/, uint32_t n_segments,
                            uint32_t rows_per_segment, uint8_t *d_out, uint64_t out_cap, uint64_t *d_page_off,
                            uint32_t *d_page_len, uint64_t *total_bytes_out);
+
+/* ---- downsample / level compaction of one field column in one call (csrc/downsample.cu).  Replaces
+ * engine/record_plan.go:494-830 (FileSequenceAggregator + newProcessor: per-series, per-window min/max/sum/count/first/last)
+ * feeding engine/immutable/stream_downsample.go:454-600 (re-encode through the ordinary column builders).  The new shard has the
+ * source's series, six field columns named min_f<c>, max_f<c>, sum_f<c>, count_f<c>, first_f<c>, last_f<c> (count is an integer
+ * column, the others keep the source type), one row per window that held rows, the window start as row time, 1000-row
+ * segments.  Its pages stay in device memory: og_downsampled_desc describes them with OG_SHARD_DEVICE_DATA (the description
+ * borrows from the handle; open it with og_shard_open to query it in place), og_downsampled_export copies the page bytes to
+ * the host for a file writer. ---- */
+typedef struct og_downsampled og_downsampled;
+OG_API int og_downsample(og_shard *s, uint32_t column, int64_t interval, int64_t tmin, int64_t tmax, og_downsampled **out);
+OG_API int og_downsampled_desc(const og_downsampled *d, og_shard_desc *desc, uint64_t *rows /* may be NULL */);
+OG_API int og_downsampled_export(const og_downsampled *d, uint8_t *host_data /* desc->data_len bytes */);
+OG_API void og_downsampled_free(og_downsampled *d);
 
 #ifdef __cplusplus
 }

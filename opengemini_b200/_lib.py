@@ -101,6 +101,7 @@ EXPORTS = [
     "og_query_abort", "og_query_destroy", "og_query_merge_dense", "og_decode_segment", "og_decode_segment_ex", "og_decode_column_device",
     "og_shard_synth", "og_shard_layout_get", "og_shard_export", "og_encode_pages",
     "og_release_cached_memory", "og_comm_unique_id", "og_comm_init_rank", "og_comm_destroy", "og_comm_info", "og_comm_allreduce_f64", "og_query_allreduce",
+    "og_downsample", "og_downsampled_desc", "og_downsampled_export", "og_downsampled_free",
     "og_tssp_parse", "og_tssp_desc", "og_tssp_measurement", "og_tssp_time_range", "og_tssp_free",
 ]
 
@@ -143,6 +144,11 @@ def lib():
     L.og_query_destroy.restype = None
     L.og_query_merge_dense.argtypes = [C.c_void_p, C.POINTER(DenseView)]
     L.og_decode_segment.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RecordView)]
+    L.og_downsample.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+    L.og_downsampled_desc.argtypes = [C.c_void_p, C.POINTER(ShardDesc), C.POINTER(C.c_uint64)]
+    L.og_downsampled_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.og_downsampled_free.argtypes = [C.c_void_p]
+    L.og_downsampled_free.restype = None
     L.og_tssp_parse.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     L.og_tssp_desc.argtypes = [C.c_void_p, C.POINTER(ShardDesc)]
     L.og_tssp_measurement.argtypes = [C.c_void_p]

@@ -144,6 +144,12 @@ class Shard:
                 "og_shard_export")
         return out
 
+    def downsample(self, column, interval, tmin, tmax):
+        """og_downsample: per-series min/max/sum/count/first/last of `column` per window -> re-encoded pages, in one library call."""
+        h = C.c_void_p()
+        L.check(L.lib().og_downsample(self.h, column, interval, tmin, tmax, C.byref(h)), "og_downsample")
+        return Downsampled(h.value)
+
     def decode_segment(self, seg, descending=False):
         rv = L.RecordView()
         L.check(L.lib().og_decode_segment_ex(self.h, seg, 1 if descending else 0, C.byref(rv)), "og_decode_segment_ex")
@@ -152,6 +158,37 @@ class Shard:
     def close(self):
         if self.h:
             L.lib().og_shard_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Downsampled:
+    """Result of Shard.downsample: a shard description whose pages live in device memory (owned by this handle)."""
+
+    def __init__(self, h):
+        self.h = h
+        self.desc = L.ShardDesc()
+        rows = C.c_uint64()
+        L.check(L.lib().og_downsampled_desc(self.h, C.byref(self.desc), C.byref(rows)), "og_downsampled_desc")
+        self.rows = rows.value
+
+    def open(self):
+        """Open the new shard in place (zero-copy: OG_SHARD_DEVICE_DATA); this object must outlive the returned Shard."""
+        return Shard.open_desc(self.desc, keepalive=self)
+
+    def export(self):
+        out = np.empty(max(1, self.desc.data_len), np.uint8)
+        L.check(L.lib().og_downsampled_export(self.h, out.ctypes.data), "og_downsampled_export")
+        return out[:self.desc.data_len]
+
+    def close(self):
+        if self.h:
+            L.lib().og_downsampled_free(self.h)
             self.h = None
 
     def __del__(self):

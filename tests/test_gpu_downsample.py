@@ -75,3 +75,45 @@ def test_downsample_reencode_roundtrip():
     a, b = q1["cols"][2]["values"][m], q0["cols"][2]["values"][m]
     assert np.all(np.abs(a - b) <= 1e-9 * np.abs(b))  # re-associated float sums: north_star tolerance
     ds.close(); sh.close()
+
+
+@pytest.mark.parametrize("typ,dist", [(L.TYPE_FLOAT, L.SYNTH_F_HI), (L.TYPE_INT, L.SYNTH_INT_WALK)])
+def test_c_abi_downsample_equals_the_checked_pass(typ, dist):
+    """og_downsample (one C-ABI call, csrc/downsample.cu) must produce the pages and the directory of the pass that the test
+    above checks against the oracle (opengemini_b200/downsample.py, same query and encoders, torch for the compaction), and the
+    new shard must open in place."""
+    from opengemini_b200 import AggQuery, Shard
+    from opengemini_b200.downsample import downsample
+
+    ns, rows, ivl = 5, 4321, 3 * SEC
+    cols = [(L.TYPE_BOOL, L.SYNTH_BOOL, 0), (typ, dist, 0)]
+    sh = Shard.synth(ns, rows, cols, t0=T0, dt=SEC, seed=13)
+    tmin, tmax = T0 + 5 * SEC, T0 + (rows - 11) * SEC
+    want = downsample(sh, 1, ivl, tmin, tmax, col_type=typ)
+    got = sh.downsample(1, ivl, tmin, tmax)
+    d = got.desc
+    nseg = len(want["seg_tmin"])
+    assert got.rows == want["rows"] and d.n_series == ns and d.n_segments == nseg and d.n_columns == 6
+    assert d.data_len == want["data_len"]
+    assert [d.series_seg_begin[i] for i in range(ns + 1)] == list(want["series_seg_begin"])
+    assert [d.seg_tmin[g] for g in range(nseg)] == list(want["seg_tmin"]) and [d.seg_tmax[g] for g in range(nseg)] == list(want["seg_tmax"])
+    data, ref = got.export(), want["data"].cpu().numpy()
+    for k, (name, ctyp, po, pl) in enumerate(want["columns"] + [("time", L.TYPE_INT, want["time_page_off"], want["time_page_len"])]):
+        off = d.time_page_off if k == 6 else d.columns[k].page_off
+        ln = d.time_page_len if k == 6 else d.columns[k].page_len
+        if k < 6:
+            assert d.columns[k].name.decode() == name and d.columns[k].type == ctyp
+        for g in range(nseg):
+            assert ln[g] == pl[g], (name, g)
+            assert data[off[g]:off[g] + ln[g]].tobytes() == ref[po[g]:po[g] + pl[g]].tobytes(), (name, g)
+    ds = got.open()
+    q1 = AggQuery(ds, [("sum", 3), ("min", 0), ("max", 1)], 0, tmin - ivl, tmax).run().dense_host()
+    q0 = AggQuery(sh, [("count", 1), ("min", 1), ("max", 1)], 0, tmin, tmax).run().dense_host()
+    for k in range(3):
+        assert int(q1["cols"][k]["values"].view(np.uint64)[0]) == int(q0["cols"][k]["values"].view(np.uint64)[0]), k
+    ds.close(); got.close(); sh.close()
+    # a range without rows: an empty shard, not an error
+    sh2 = Shard.synth(2, 100, [(L.TYPE_FLOAT, L.SYNTH_F_HI, 0)], t0=T0, dt=SEC, seed=1)
+    e = sh2.downsample(0, ivl, T0 + 10_000 * SEC, T0 + 20_000 * SEC)
+    assert e.rows == 0 and e.desc.n_segments == 0 and e.desc.n_series == 2
+    e.close(); sh2.close()
